@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the move-evaluation hot path (BASELINE.json metric: candidate moves scored/sec).
+
+A "step" = one local-search step of EVERY chain: the full swap neighbourhood of each chain
+(n(n-1)/2 candidates) is delta-scored, the best move selected and accepted on device.
+Workload at N=1 = BASELINE.json configs[1]: n-queens n=10,000, 4096 restart chains per GPU.
+N>1 (torchrun, one rank per GPU): chains sharded, 4096 per GPU (weak scaling), no data-path
+collective; one NCCL min-allreduce of the packed best key + elite broadcast per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate moves scored/sec"
+UNIT = "moves/s"
+BYTES_PER_MOVE = {"nq_swap_u16": 20, "nq_change_u16": 14}  # SURVEY 8(d) contract figures
+HBM_FALLBACK_GBS = 6650.0
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(args):
+    return dict(n=args.n, chains_per_gpu=args.chains, neighbourhood="swap")
+
+
+def cpu_reference_run(args, steps, warmup, threads):
+    """The reference's CPU formulation (clone + full O(n^2) re-score per candidate,
+    local_search.rs:315-322 + nqueens lib.rs:74-87) restated in oracle/cs_oracle.c, on a
+    bounded sample of the same workload, all host threads."""
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    n = args.n
+    rows = orc.nq_init_perm(args.seed, 0, n)
+    rng = np.random.default_rng(0)
+    per_step = args.cpu_sample
+    a = rng.integers(0, n - 1, size=per_step)
+    b = a + 1 + rng.integers(0, n, size=per_step) % (n - 1 - a)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        k, _ = orc.nq_baseline_sample(rows, a, b, threads)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return per_step * len(times) / tot, 1e3 * tot / len(times), per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, warmup = args.steps, args.warmup
+    # bound the run: ~per_step candidates x 50 ms / threads per step
+    v, ms, per_step = cpu_reference_run(args, steps, warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"nqueens n={args.n}, swap neighbourhood, clone + full re-score per "
+                               f"candidate (the reference's CPU path), {per_step} candidates/step sample"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} swap candidates of one n={args.n} chain per step, "
+                                   f"{steps} steps, OpenMP over candidates"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000)
+    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-sample", type=int, default=512, help="candidates per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+
+    import constraint_solver_b200 as cs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, chains = args.n, args.chains
+    eng = cs.NQueensChains(n, chains, seed=args.seed, chain_offset=rank * chains, device=local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.init_random()
+
+    from constraint_solver_b200.dist import BestExchange
+
+    xchg = BestExchange(eng, dist, rank, world, chains) if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        st = eng.step(1)
+        if xchg is not None:
+            xchg.sync()
+        return st
+
+    for _ in range(args.warmup):
+        one_step()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    moves = 0
+    kernel_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        st = one_step()
+        moves += st.moves_scored
+        kernel_ms += st.device_ms
+        launches += st.kernel_launches
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms, float(moves), kernel_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, total_moves, kernel_ms_max = float(tmax[0]), float(tsum[1]), float(tmax[2])
+    else:
+        total_moves, kernel_ms_max = float(moves), kernel_ms
+    value = total_moves / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned int64, the reference's type)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((chains, n), dtype=torch.int64, pin_memory=True)
+        host.copy_(torch.from_numpy(eng.get_chains()))
+        scores = np.empty(chains, dtype=np.int64)
+        for _ in range(1):
+            eng.set_chains_ptr(host.data_ptr(), chains)
+            eng.step(1)
+        barrier()
+        t0 = time.perf_counter()
+        e_moves = 0
+        for _ in range(args.steps):
+            eng.set_chains_ptr(host.data_ptr(), chains)   # H2D of this step's inputs
+            st = eng.step(1)                               # the hot path
+            scores = eng.scores()                          # D2H of the step's result
+            if xchg is not None:
+                xchg.sync()
+            e_moves += st.moves_scored
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt, float(e_moves)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            dt, e_total = float(a[0]), float(b[1])
+        else:
+            e_total = float(e_moves)
+        e2e = {"value": e_total / dt, "unit": UNIT, "h2d_bytes_per_step": chains * n * 8,
+               "d2h_bytes_per_step": chains * 8 + 48}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = _peaks()
+    # roofline of the dominant kernel (nq_step_kernel): algorithmic bytes = 20 B per swap
+    # candidate (10 u16 state words: rows[i], rows[j], 4 old-line + 4 new-line counters)
+    per_launch_moves = float(moves) / args.steps
+    avg_launch_s = (kernel_ms / args.steps) * 1e-3
+    achieved = per_launch_moves * BYTES_PER_MOVE["nq_swap_u16"] / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": _ncu_traffic(),
+                "kernel": "nq_step_kernel", "peak_source": peak_src,
+                "note": "state is staged once per chain-step in shared memory, so algorithmic "
+                        "GB/s is served on-chip and may exceed the HBM peak; the binding "
+                        "resource is shared-memory bandwidth (see DESIGN.md)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"nqueens n={n}, {chains} restart chains per GPU, full swap "
+                               f"neighbourhood ({n * (n - 1) // 2} candidates) delta-scored per chain-step",
+                   "parallelism": f"chains sharded x{world}" if world > 1 else "1 GPU",
+                   "l2": "chain state 2x82 MB > 126 MB L2; kernel is shared-memory resident "
+                         "(HBM traffic << 1% of time), no flush needed",
+                   "init": "Philox4x32-10 Fisher-Yates, key=(seed 42, global chain id)"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "kernel_ms_per_step": kernel_ms / args.steps,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, ms, per = cpu_reference_run(args, 3, 1, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{per} swap candidates/step x 3 steps of one n={n} chain, "
+                                          "clone + full O(n^2) re-score each (reference formulation), "
+                                          "OpenMP over candidates"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """dram bytes per launch of nq_step_kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("nq_step_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+if __name__ == "__main__":
+    main()

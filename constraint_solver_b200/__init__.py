@@ -1,0 +1,23 @@
+"""constraint_solver_b200 -- B200-native (sm_100a) move-evaluation hot path of
+asimihsan/constraint-solver's local-search crate, behind a C ABI (include/cs_b200.h).
+
+(The directory is spelled with an underscore so it is importable; the task text calls the
+package `constraint-solver_b200`.)
+"""
+from . import _lib
+from ._lib import CsError, load
+from .nqueens import (CHANGE, SWAP, NQueensChains, NQueensInitialSolutionGenerator,
+                      NQueensMoveProposer, NQueensScore, NQueensSolution,
+                      NQueensSolutionScoreCalculator, ScoredSolution, StepStats)
+from .local_search import LocalSearch
+
+
+def philox4x32_10(seed: int, chain: int, purpose: int, counter: int):
+    import ctypes as C
+    out = (C.c_uint32 * 4)()
+    load().cs_philox4x32_10(seed, chain, purpose, counter, out)
+    return [int(x) for x in out]
+
+
+def device_count() -> int:
+    return int(load().cs_device_count())

@@ -1,0 +1,671 @@
+// C ABI (include/cs_b200.h) over the sm_100a chain kernels.  No CPU fallback: every entry
+// point that computes needs a CUDA device and says so loudly when there is none.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cs_b200.h"
+#include "nq_kernels.cuh"
+#include "philox.cuh"
+
+using namespace csb;
+
+// ------------------------------------------------------------------ helpers
+namespace {
+
+struct CudaFail {
+    cudaError_t e;
+    const char* what;
+    int line;
+};
+
+#define CU(expr)                                            \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) throw CudaFail{_e, #expr, __LINE__}; \
+    } while (0)
+
+struct ArgFail {
+    std::string msg;
+};
+#define REQUIRE(cond, msg)               \
+    do {                                 \
+        if (!(cond)) throw ArgFail{msg}; \
+    } while (0)
+
+struct StateFail {
+    std::string msg;
+};
+
+template <typename H, typename F>
+int32_t guarded(H* h, F&& f) {
+    if (!h) return CS_ERR_INVALID_ARG;
+    try {
+        h->err.clear();
+        CU(cudaSetDevice(h->device));
+        f();
+        return CS_OK;
+    } catch (const CudaFail& c) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at cs_api.cu:%d: %s", (int)c.e,
+                 cudaGetErrorString(c.e), c.line, c.what);
+        h->err = buf;
+        cudaGetLastError();
+        return c.e == cudaErrorMemoryAllocation ? CS_ERR_OOM : CS_ERR_CUDA;
+    } catch (const ArgFail& a) {
+        h->err = a.msg;
+        return CS_ERR_INVALID_ARG;
+    } catch (const StateFail& s) {
+        h->err = s.msg;
+        return CS_ERR_STATE;
+    } catch (const std::bad_alloc&) {
+        h->err = "host out of memory";
+        return CS_ERR_OOM;
+    } catch (...) {
+        h->err = "unknown internal error";
+        return CS_ERR_CUDA;
+    }
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// ------------------------------------------------------------------ library-wide
+extern "C" int32_t cs_abi_version(void) { return CS_ABI_VERSION; }
+
+extern "C" int32_t cs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void cs_philox4x32_10(uint64_t seed, uint32_t chain, uint32_t purpose,
+                                 uint64_t counter, uint32_t out[4]) {
+    const Philox4 r = philox_stream(seed, chain, purpose, counter);
+    for (int k = 0; k < 4; ++k) out[k] = r.v[k];
+}
+
+extern "C" const char* cs_status_string(int32_t s) {
+    switch (s) {
+        case CS_OK: return "ok";
+        case CS_ERR_INVALID_ARG: return "invalid argument";
+        case CS_ERR_CUDA: return "CUDA error";
+        case CS_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case CS_ERR_OOM: return "out of memory";
+        case CS_ERR_STATE: return "invalid handle state";
+        case CS_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+// ------------------------------------------------------------------ n-queens handle
+struct cs_nq_handle {
+    cs_nq_config cfg{};
+    int device = 0;
+    int n_pad = 0;
+    int sm_count = 0;
+    int threads = NQ_THREADS;
+    size_t smem = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint16_t* d_rows = nullptr;
+    uint16_t* d_best_rows = nullptr;
+    NqChainState* d_st = nullptr;
+    NqTraceEntry* d_trace = nullptr;
+    unsigned int* d_work = nullptr;
+    unsigned long long* d_totals = nullptr;  // [2] moves, steps of the current call
+    NqStats* d_stats = nullptr;
+    NqStats* h_stats = nullptr;  // pinned
+    unsigned long long* h_totals = nullptr;  // pinned [2]
+    long long* d_stage = nullptr;
+    size_t stage_elems = 0;
+    int* d_bad = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool scored = false;  // chain scores valid
+    std::string err;
+};
+
+namespace {
+
+constexpr int NQ_TI = 4;
+
+NqParams nq_params(cs_nq_handle* h, int first, int count) {
+    NqParams p{};
+    p.n = (int)h->cfg.n;
+    p.n_pad = h->n_pad;
+    p.first_chain = first;
+    p.n_chains = count;
+    p.rows = h->d_rows;
+    p.best_rows = h->d_best_rows;
+    p.st = h->d_st;
+    p.trace = h->d_trace;
+    p.trace_cap = (int)h->cfg.trace_capacity;
+    p.work_counter = h->d_work;
+    p.totals = h->d_totals;
+    p.max_steps = 0;
+    p.allow_no_improve = 0;
+    p.ls_mode = 0;
+    p.kind = (int)h->cfg.neighbourhood;
+    p.dump = nullptr;
+    return p;
+}
+
+void nq_free(cs_nq_handle* h) {
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_rows);
+    cudaFree(h->d_best_rows);
+    cudaFree(h->d_st);
+    cudaFree(h->d_trace);
+    cudaFree(h->d_work);
+    cudaFree(h->d_totals);
+    cudaFree(h->d_stats);
+    cudaFree(h->d_stage);
+    cudaFree(h->d_bad);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_totals) cudaFreeHost(h->h_totals);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+}
+
+void nq_check_range(cs_nq_handle* h, uint32_t first, uint32_t count) {
+    REQUIRE(count > 0 && first < h->cfg.n_chains && count <= h->cfg.n_chains - first,
+            "chain range outside [0, n_chains)");
+}
+
+// (re)compute score / best / permutation flag of a chain range after its rows changed
+void nq_rescore(cs_nq_handle* h, int first, int count) {
+    NqParams p = nq_params(h, first, count);
+    const int grid = count < h->sm_count ? count : h->sm_count;
+    nq_rescore_kernel<<<grid, h->threads, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+}
+
+void nq_refresh_stats(cs_nq_handle* h) {
+    nq_stats_kernel<<<1, 1024, 0, h->stream>>>(h->d_st, (int)h->cfg.n_chains,
+                                                h->cfg.chain_offset, h->d_stats);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(NqStats), cudaMemcpyDeviceToHost,
+                       h->stream));
+}
+
+void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
+            unsigned long long allow, int ls_mode, cs_step_stats* stats) {
+    if (!h->scored) throw StateFail{"chains have no solution yet: call cs_nq_init_random or cs_nq_set_chains first"};
+    NqParams p = nq_params(h, first, count);
+    p.max_steps = max_steps;
+    p.allow_no_improve = allow;
+    p.ls_mode = ls_mode;
+    CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+    CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
+    const int grid = count < h->sm_count ? count : h->sm_count;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    nq_step_kernel<NQ_TI><<<grid, h->threads, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    nq_refresh_stats(h);
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (stats) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        stats->moves_scored = h->h_totals[0];
+        stats->steps_accepted = h->h_totals[1];
+        stats->best_score = h->h_stats->best_score;
+        stats->best_chain = h->h_stats->best_chain;
+        stats->chains_at_best = h->h_stats->chains_at_best;
+        stats->device_ms = ms;
+        stats->kernel_launches = 2;
+    }
+}
+
+void nq_upload(cs_nq_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
+    const size_t n = h->cfg.n;
+    const size_t per = h->stage_elems / n;  // chains per staging pass
+    CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+    for (uint32_t done = 0; done < count;) {
+        const uint32_t c = (uint32_t)((count - done) < per ? (count - done) : per);
+        CU(cudaMemcpyAsync(h->d_stage, rows + (size_t)done * n, (size_t)c * n * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, h->stream));
+        const long long total = (long long)c * h->n_pad;
+        const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        nq_pack_rows_kernel<<<grid, 256, 0, h->stream>>>(
+            h->d_stage, h->d_rows + (size_t)(first + done) * h->n_pad, (int)n, h->n_pad, (int)c,
+            h->d_bad);
+        CU(cudaGetLastError());
+        // the staging buffer is reused by the next pass
+        CU(cudaStreamSynchronize(h->stream));
+        done += c;
+    }
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    REQUIRE(!bad, "row value outside [0, n)");
+}
+
+void nq_download(cs_nq_handle* h, const uint16_t* src, uint32_t first, uint32_t count,
+                 int64_t* rows) {
+    const size_t n = h->cfg.n;
+    const size_t per = h->stage_elems / n;
+    for (uint32_t done = 0; done < count;) {
+        const uint32_t c = (uint32_t)((count - done) < per ? (count - done) : per);
+        const long long total = (long long)c * (long long)n;
+        const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        nq_unpack_rows_kernel<<<grid, 256, 0, h->stream>>>(
+            src + (size_t)(first + done) * h->n_pad, h->d_stage, (int)n, h->n_pad, (int)c);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(rows + (size_t)done * n, h->d_stage, (size_t)c * n * sizeof(int64_t),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        done += c;
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
+    if (!cfg || !out) return CS_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->n < 1 || cfg->n_chains < 1 || cfg->neighbourhood > CS_NQ_CHANGE)
+        return CS_ERR_INVALID_ARG;
+    if (cfg->n > CS_NQ_MAX_N_SMEM) return CS_ERR_UNSUPPORTED;
+    if ((uint64_t)cfg->chain_offset + cfg->n_chains > 0xffffffffull) return CS_ERR_INVALID_ARG;
+    int ndev = cs_device_count();
+    if (ndev <= 0) return CS_ERR_NO_DEVICE;
+    int dev = cfg->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) return CS_ERR_NO_DEVICE;
+    }
+    if (dev >= ndev) return CS_ERR_INVALID_ARG;
+    cs_nq_handle* h = new (std::nothrow) cs_nq_handle();
+    if (!h) return CS_ERR_OOM;
+    h->cfg = *cfg;
+    h->device = dev;
+    const int32_t rc = guarded(h, [&] {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, dev));
+        h->sm_count = prop.multiProcessorCount;
+        const int n = (int)cfg->n;
+        h->n_pad = round_up(n, NQ_PAD);
+        h->smem = nq_smem_bytes(h->n_pad);
+        REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin,
+                "board does not fit the shared-memory chain kernel on this device");
+        h->threads = n <= 96 ? 128 : n <= 512 ? 256 : n <= 2048 ? 512 : 1024;
+        CU(cudaFuncSetAttribute(nq_step_kernel<NQ_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)h->smem));
+        CU(cudaFuncSetAttribute(nq_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)h->smem));
+        CU(cudaFuncSetAttribute(nq_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)h->smem));
+        // resident CTAs: as many as fit, so small boards run several chains per SM
+        int per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nq_step_kernel<NQ_TI>,
+                                                         h->threads, h->smem));
+        if (per_sm < 1) per_sm = 1;
+        h->sm_count *= per_sm;  // sm_count now = resident CTA slots (grid cap)
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+        const size_t nc = cfg->n_chains;
+        CU(cudaMalloc(&h->d_rows, nc * h->n_pad * sizeof(uint16_t)));
+        CU(cudaMalloc(&h->d_best_rows, nc * h->n_pad * sizeof(uint16_t)));
+        CU(cudaMalloc(&h->d_st, nc * sizeof(NqChainState)));
+        if (cfg->trace_capacity)
+            CU(cudaMalloc(&h->d_trace, nc * cfg->trace_capacity * sizeof(NqTraceEntry)));
+        CU(cudaMalloc(&h->d_work, sizeof(unsigned int)));
+        CU(cudaMalloc(&h->d_totals, 2 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_stats, sizeof(NqStats)));
+        CU(cudaMalloc(&h->d_bad, sizeof(int)));
+        CU(cudaMallocHost(&h->h_stats, sizeof(NqStats)));
+        CU(cudaMallocHost(&h->h_totals, 2 * sizeof(unsigned long long)));
+        // staging for int64 <-> u16 conversion: whole chains, ~64 MiB or one chain
+        size_t per = (size_t)(64u << 20) / (n * sizeof(int64_t));
+        if (per < 1) per = 1;
+        if (per > nc) per = nc;
+        h->stage_elems = per * n;
+        CU(cudaMalloc(&h->d_stage, h->stage_elems * sizeof(int64_t)));
+        CU(cudaEventCreate(&h->ev0));
+        CU(cudaEventCreate(&h->ev1));
+        CU(cudaMemsetAsync(h->d_rows, 0, nc * h->n_pad * sizeof(uint16_t), h->stream));
+        CU(cudaMemsetAsync(h->d_best_rows, 0, nc * h->n_pad * sizeof(uint16_t), h->stream));
+        nq_reset_state_kernel<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>(h->d_st, 0, (int)nc);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    });
+    if (rc != CS_OK) {
+        fprintf(stderr, "cs_nq_create failed: %s\n", h->err.c_str());
+        nq_free(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_nq_destroy(cs_nq_handle* h) {
+    if (!h) return CS_ERR_INVALID_ARG;
+    nq_free(h);
+    delete h;
+    return CS_OK;
+}
+
+extern "C" const char* cs_nq_last_error(const cs_nq_handle* h) { return h ? h->err.c_str() : ""; }
+
+extern "C" int32_t cs_nq_set_stream(cs_nq_handle* h, void* s) {
+    return guarded(h, [&] {
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->own_stream) {
+            CU(cudaStreamDestroy(h->stream));
+            h->own_stream = false;
+        }
+        h->stream = (cudaStream_t)s;
+    });
+}
+
+extern "C" int32_t cs_nq_init_random(cs_nq_handle* h) {
+    return guarded(h, [&] {
+        const int nc = (int)h->cfg.n_chains;
+        nq_init_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(h->d_rows, h->d_st, (int)h->cfg.n,
+                                                              h->n_pad, nc, h->cfg.seed,
+                                                              h->cfg.chain_offset);
+        CU(cudaGetLastError());
+        nq_rescore(h, 0, nc);
+        nq_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first, uint32_t count,
+                                    const int64_t* rows) {
+    return guarded(h, [&] {
+        REQUIRE(rows, "rows is NULL");
+        nq_check_range(h, first, count);
+        nq_upload(h, first, count, rows);
+        nq_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first,
+                                                                          (int)count);
+        CU(cudaGetLastError());
+        nq_rescore(h, (int)first, (int)count);
+        if (!h->scored && !(first == 0 && count == h->cfg.n_chains)) {
+            // chains never given a solution hold the all-zero board; score them too
+            nq_rescore(h, 0, (int)h->cfg.n_chains);
+        }
+        nq_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_nq_get_chains(cs_nq_handle* h, uint32_t first, uint32_t count,
+                                    int64_t* rows) {
+    return guarded(h, [&] {
+        REQUIRE(rows, "rows is NULL");
+        nq_check_range(h, first, count);
+        nq_download(h, h->d_rows, first, count, rows);
+    });
+}
+
+extern "C" int32_t cs_nq_get_best_chains(cs_nq_handle* h, uint32_t first, uint32_t count,
+                                         int64_t* rows, int64_t* best_scores) {
+    return guarded(h, [&] {
+        nq_check_range(h, first, count);
+        if (rows) nq_download(h, h->d_best_rows, first, count, rows);
+        if (best_scores) {
+            std::vector<NqChainState> st(count);
+            CU(cudaMemcpyAsync(st.data(), h->d_st + first, count * sizeof(NqChainState),
+                               cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            for (uint32_t k = 0; k < count; ++k) best_scores[k] = st[k].best_score;
+        }
+    });
+}
+
+extern "C" int32_t cs_nq_get_scores(cs_nq_handle* h, int64_t* scores) {
+    return guarded(h, [&] {
+        REQUIRE(scores, "scores is NULL");
+        std::vector<NqChainState> st(h->cfg.n_chains);
+        CU(cudaMemcpyAsync(st.data(), h->d_st, st.size() * sizeof(NqChainState),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (size_t k = 0; k < st.size(); ++k) scores[k] = st[k].score;
+    });
+}
+
+extern "C" int32_t cs_nq_get_status(cs_nq_handle* h, uint32_t* status) {
+    return guarded(h, [&] {
+        REQUIRE(status, "status is NULL");
+        std::vector<NqChainState> st(h->cfg.n_chains);
+        CU(cudaMemcpyAsync(st.data(), h->d_st, st.size() * sizeof(NqChainState),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (size_t k = 0; k < st.size(); ++k) status[k] = st[k].status;
+    });
+}
+
+extern "C" int32_t cs_nq_score_full(cs_nq_handle* h, uint32_t chain, int64_t* score) {
+    return guarded(h, [&] {
+        REQUIRE(score, "score is NULL");
+        nq_check_range(h, chain, 1);
+        unsigned long long* d_pairs = (unsigned long long*)h->d_totals;  // reuse, restored below
+        CU(cudaMemsetAsync(d_pairs, 0, sizeof(unsigned long long), h->stream));
+        const int n = (int)h->cfg.n;
+        const int grid = n < 2048 ? (n > 0 ? n : 1) : 2048;
+        nq_pair_score_kernel<<<grid, 256, 0, h->stream>>>(h->d_rows + (size_t)chain * h->n_pad, n,
+                                                          d_pairs);
+        CU(cudaGetLastError());
+        unsigned long long pairs = 0;
+        CU(cudaMemcpyAsync(&pairs, d_pairs, sizeof pairs, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        *score = 2 * (int64_t)pairs;
+    });
+}
+
+extern "C" int32_t cs_nq_eval_moves(cs_nq_handle* h, uint32_t chain, uint32_t kind,
+                                    const cs_move* moves, uint64_t n_moves, int64_t* delta) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(kind <= CS_NQ_CHANGE, "unknown move kind");
+        if (n_moves == 0) return;
+        REQUIRE(moves && delta, "moves/delta is NULL");
+        const uint32_t n = h->cfg.n;
+        for (uint64_t k = 0; k < n_moves; ++k)
+            REQUIRE(moves[k].a < n && moves[k].b < n, "move index outside the board");
+        uint2* d_moves = nullptr;
+        long long* d_delta = nullptr;
+        CU(cudaMalloc(&d_moves, n_moves * sizeof(uint2)));
+        cudaError_t e = cudaMalloc(&d_delta, n_moves * sizeof(long long));
+        if (e != cudaSuccess) {
+            cudaFree(d_moves);
+            CU(e);
+        }
+        try {
+            CU(cudaMemcpyAsync(d_moves, moves, n_moves * sizeof(uint2), cudaMemcpyHostToDevice,
+                               h->stream));
+            NqParams p = nq_params(h, 0, (int)h->cfg.n_chains);
+            nq_eval_kernel<<<1, h->threads, h->smem, h->stream>>>(p, (int)chain, (int)kind, d_moves,
+                                                                  n_moves, d_delta);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(delta, d_delta, n_moves * sizeof(long long), cudaMemcpyDeviceToHost,
+                               h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } catch (...) {
+            cudaFree(d_moves);
+            cudaFree(d_delta);
+            throw;
+        }
+        cudaFree(d_moves);
+        cudaFree(d_delta);
+    });
+}
+
+extern "C" int32_t cs_nq_enumerate(cs_nq_handle* h, uint32_t chain, cs_move* moves, uint64_t cap,
+                                   uint64_t* n_out) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        const uint32_t n = h->cfg.n;
+        std::vector<int64_t> rows(n);
+        nq_download(h, h->d_rows, chain, 1, rows.data());
+        uint64_t k = 0;
+        if (h->cfg.neighbourhood == CS_NQ_SWAP) {
+            for (uint32_t i = 0; i < n; ++i)
+                for (uint32_t j = i + 1; j < n; ++j) {
+                    if (rows[i] == rows[j]) continue;
+                    if (moves && k < cap) moves[k] = cs_move{i, j};
+                    ++k;
+                }
+        } else {
+            for (uint32_t c = 0; c < n; ++c)
+                for (uint32_t v = 0; v < n; ++v) {
+                    if (rows[c] == (int64_t)v) continue;
+                    if (moves && k < cap) moves[k] = cs_move{c, v};
+                    ++k;
+                }
+        }
+        *n_out = k;
+    });
+}
+
+extern "C" int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, int64_t* delta,
+                                              uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        const uint64_t n = h->cfg.n;
+        const uint64_t cnt = h->cfg.neighbourhood == CS_NQ_SWAP ? n * (n - 1) / 2 : n * n;
+        *n_out = cnt;
+        if (!delta || cnt == 0) return;
+        REQUIRE(cap >= cnt, "delta buffer too small");
+        long long* d_dump = nullptr;
+        CU(cudaMalloc(&d_dump, cnt * sizeof(long long)));
+        try {
+            CU(cudaMemsetAsync(d_dump, 0x7f, cnt * sizeof(long long), h->stream));
+            NqParams p = nq_params(h, (int)chain, 1);
+            p.max_steps = 1;
+            p.dump = d_dump;
+            CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+            nq_step_kernel<NQ_TI><<<1, h->threads, h->smem, h->stream>>>(p);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(delta, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost,
+                               h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } catch (...) {
+            cudaFree(d_dump);
+            throw;
+        }
+        cudaFree(d_dump);
+    });
+}
+
+extern "C" int32_t cs_nq_step(cs_nq_handle* h, uint32_t n_steps, cs_step_stats* stats) {
+    return guarded(h, [&] {
+        nq_run(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0, stats);
+    });
+}
+
+extern "C" int32_t cs_nq_local_search(cs_nq_handle* h, uint64_t allow, uint64_t max_iterations,
+                                      cs_step_stats* stats) {
+    return guarded(h, [&] {
+        nq_run(h, 0, (int)h->cfg.n_chains, max_iterations, allow, 1, stats);
+    });
+}
+
+extern "C" int32_t cs_nq_local_search_one(cs_nq_handle* h, const int64_t* start, uint64_t allow,
+                                          uint64_t max_iterations, int64_t* best,
+                                          int64_t* best_score) {
+    return guarded(h, [&] {
+        REQUIRE(start, "start is NULL");
+        nq_upload(h, 0, 1, start);
+        nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, 0, 1);
+        CU(cudaGetLastError());
+        nq_rescore(h, 0, h->scored ? 1 : (int)h->cfg.n_chains);
+        h->scored = true;
+        nq_run(h, 0, 1, max_iterations, allow, 1, nullptr);
+        if (best) nq_download(h, h->d_best_rows, 0, 1, best);
+        if (best_score) {
+            NqChainState st;
+            CU(cudaMemcpyAsync(&st, h->d_st, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            *best_score = st.best_score;
+        }
+    });
+}
+
+extern "C" int32_t cs_nq_get_trace(cs_nq_handle* h, uint32_t chain, cs_move* moves,
+                                   int64_t* score_after, uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        NqChainState st;
+        CU(cudaMemcpyAsync(&st, h->d_st + chain, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        *n_out = st.steps;
+        uint64_t k = st.steps;
+        if (k > h->cfg.trace_capacity) k = h->cfg.trace_capacity;
+        if (k > cap) k = cap;
+        if (k == 0) return;
+        std::vector<NqTraceEntry> t(k);
+        CU(cudaMemcpyAsync(t.data(), h->d_trace + (size_t)chain * h->cfg.trace_capacity,
+                           k * sizeof(NqTraceEntry), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint64_t q = 0; q < k; ++q) {
+            if (moves) moves[q] = cs_move{t[q].a, t[q].b};
+            if (score_after) score_after[q] = t[q].score_after;
+        }
+    });
+}
+
+extern "C" int32_t cs_nq_best(cs_nq_handle* h, int64_t* rows, int64_t* score, uint32_t* chain) {
+    return guarded(h, [&] {
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        nq_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        if (score) *score = h->h_stats->best_score;
+        if (chain) *chain = h->h_stats->best_chain;
+        if (rows) nq_download(h, h->d_rows, h->h_stats->best_chain, 1, rows);
+    });
+}
+
+extern "C" int32_t cs_nq_best_key_device_ptr(cs_nq_handle* h, void** dptr) {
+    return guarded(h, [&] {
+        REQUIRE(dptr, "dptr is NULL");
+        *dptr = (void*)&h->d_stats->best_key;
+    });
+}
+
+extern "C" int32_t cs_nq_chain_device_ptr(cs_nq_handle* h, uint32_t chain, void** dptr,
+                                          uint32_t* stride_elems) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(dptr, "dptr is NULL");
+        *dptr = (void*)(h->d_rows + (size_t)chain * h->n_pad);
+        if (stride_elems) *stride_elems = (uint32_t)h->n_pad;
+    });
+}
+
+extern "C" int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain,
+                                              const void* d_rows_u16) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(d_rows_u16, "d_rows_u16 is NULL");
+        CU(cudaMemcpyAsync(h->d_rows + (size_t)chain * h->n_pad, d_rows_u16,
+                           (size_t)h->cfg.n * sizeof(uint16_t), cudaMemcpyDeviceToDevice,
+                           h->stream));
+        nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, (int)chain, 1);
+        CU(cudaGetLastError());
+        nq_rescore(h, (int)chain, 1);
+        nq_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+    });
+}

@@ -1,0 +1,70 @@
+"""Multi-GPU plumbing: chains are sharded across ranks (one process per GPU, chain k of rank r
+has global id r * chains_per_rank + k == its Philox stream), so the data path needs NO
+collective.  The only exchange is the periodic best-score min-allreduce of the packed key
+((score << 32) | global chain id) followed by the elite broadcast from the owning rank
+(SURVEY 8e).  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the transport.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (ptr, False), "version": 2}
+
+
+def device_view(ptr: int, shape, typestr: str, device) -> torch.Tensor:
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+def owner_of(key: int, chains_per_rank: int):
+    """(score, owning rank, local chain) of a packed best key."""
+    gid = key & 0xFFFFFFFF
+    return key >> 32, gid // chains_per_rank, gid % chains_per_rank
+
+
+def exchange_best(dist, local_key: torch.Tensor, rows_of, elite: torch.Tensor, rank: int,
+                  chains_per_rank: int):
+    """min-allreduce the packed key, then broadcast the winner's solution into `elite`.
+
+    local_key: 1-element int64 tensor (this rank's best key); rows_of(local_chain) -> tensor
+    shaped like `elite` holding that chain's solution.  Returns (score, global chain id).
+    """
+    key = local_key.clone()
+    dist.all_reduce(key, op=dist.ReduceOp.MIN)
+    k = int(key.item())
+    score, owner, local = owner_of(k, chains_per_rank)
+    if owner == rank:
+        elite.copy_(rows_of(local))
+    dist.broadcast(elite.view(torch.uint8), src=owner)  # byte view: no int16 in NCCL/gloo
+    return score, k & 0xFFFFFFFF
+
+
+class BestExchange:
+    """exchange_best bound to an NQueensChains engine running on torch's current stream."""
+
+    def __init__(self, eng, dist, rank: int, world: int, chains_per_rank: int):
+        self.eng, self.dist, self.rank, self.world = eng, dist, rank, world
+        self.cpr = chains_per_rank
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        self.key = device_view(eng.best_key_device_ptr(), (1,), "<i8", dev)
+        self.elite = torch.zeros(eng.n, dtype=torch.int16, device=dev)
+        self.best_score = None
+        self.best_chain = None
+
+    def _rows_of(self, local_chain: int) -> torch.Tensor:
+        ptr, _ = self.eng.chain_device_ptr(local_chain)
+        return device_view(ptr, (self.eng.n,), "<i2", self.dev)
+
+    def sync(self, inject_into_worst: bool = False):
+        self.best_score, self.best_chain = exchange_best(self.dist, self.key, self._rows_of,
+                                                         self.elite, self.rank, self.cpr)
+        if inject_into_worst and self.best_chain // self.cpr != self.rank:
+            worst = int(self.eng.scores().argmax())
+            self.eng.set_chain_from_device(worst, self.elite.data_ptr())
+        return self.best_score, self.best_chain

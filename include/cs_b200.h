@@ -1,0 +1,183 @@
+/*
+ * cs_b200.h -- C ABI of the B200-native local-search move evaluator.
+ *
+ * Drop-in boundary for ONE path of asimihsan/constraint-solver: the `local-search` crate's
+ * move-evaluation loop (enumerate neighbourhood -> score every candidate -> select best ->
+ * accept) for the nqueens and employee-scheduling plug-ins.  The reference has no FFI for this
+ * path; the seam is its generic Rust trait surface.  Each entry point below names the
+ * reference interface (file:line under the reference root) it stands in for.  The Rust-side
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int32_t status (CS_OK == 0, errors < 0); nothing unwinds or
+ *     throws across this boundary.  Where the reference would panic (unwrap on None, e.g.
+ *     examples/employee-scheduling/src/lib.rs:275) the call returns CS_ERR_INVALID_ARG.
+ *   - caller owns every in/out buffer; the library owns device memory behind the opaque
+ *     handle; no pointer is retained past a call except the handle.
+ *   - a handle is Send-not-Sync (one thread at a time), bound to ONE CUDA device; multi-GPU
+ *     is one handle per process/GPU with chain_offset giving the global chain ids.
+ *   - there is NO CPU fallback: without a CUDA device *_create returns CS_ERR_NO_DEVICE.
+ *   - solutions cross the boundary in the reference's own element type: int64_t rows
+ *     (examples/nqueens/src/lib.rs:13,19-21) and int64_t employee ids
+ *     (examples/employee-scheduling/src/lib.rs:119-122).
+ */
+#ifndef CS_B200_H
+#define CS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_OK 0
+#define CS_ERR_INVALID_ARG (-1)
+#define CS_ERR_CUDA (-2)
+#define CS_ERR_NO_DEVICE (-3)
+#define CS_ERR_OOM (-4)
+#define CS_ERR_STATE (-5)
+#define CS_ERR_UNSUPPORTED (-6)
+
+#define CS_ABI_VERSION 1
+
+/* Largest board the shared-memory-resident chain kernels take (one CTA holds rows,
+ * per-column line sums and both diagonal counter arrays in <= 227 KB). */
+#define CS_NQ_MAX_N_SMEM 16384u
+
+/* neighbourhood kinds */
+#define CS_NQ_SWAP 0u   /* exchange rows of columns i<j (new; defined against lib.rs:74-87) */
+#define CS_NQ_CHANGE 1u /* rows[col] = value, examples/nqueens/src/lib.rs:227-229 */
+
+/* per-chain status after a step / local-search call */
+#define CS_CHAIN_RUNNING 0u  /* hit the step/iteration budget */
+#define CS_CHAIN_BEST 1u     /* Score::is_best, local_search.rs:311-314 */
+#define CS_CHAIN_STALLED 2u  /* no_improvement_for >= allow_no_improvement_for, :329-334 */
+#define CS_CHAIN_EMPTY 3u    /* empty neighbourhood, :336-338 */
+
+/* Philox stream purposes (ctr[3]) */
+#define CS_PHILOX_INIT 0u
+#define CS_PHILOX_PERTURB 1u
+#define CS_PHILOX_ACCEPT 2u
+#define CS_PHILOX_HOLIDAYS 3u
+
+typedef struct cs_move {
+    uint32_t a; /* swap: column i   | change: column        */
+    uint32_t b; /* swap: column j>i | change: new row value */
+} cs_move;
+
+typedef struct cs_step_stats {
+    uint64_t moves_scored;    /* non-identity candidates delta-scored by this call (all chains) */
+    uint64_t steps_accepted;  /* accepted moves summed over chains */
+    int64_t best_score;       /* min current score over this handle's chains after the call */
+    uint32_t best_chain;      /* local index of that chain (lowest index on ties) */
+    uint32_t chains_at_best;  /* chains whose score is_best (== 0) */
+    float device_ms;          /* CUDA-event time of this call's kernels on the handle's stream */
+    uint32_t kernel_launches; /* kernels this call launched */
+} cs_step_stats;
+
+/* ------------------------------------------------------------------ library-wide */
+int32_t cs_abi_version(void);
+/* number of visible CUDA devices (0 when there is no driver/GPU) */
+int32_t cs_device_count(void);
+/* Host mirror of the device RNG so any chain can be replayed on the CPU.
+ * key = {seed lo, seed hi}; ctr = {counter lo, counter hi, chain, purpose}.
+ * Stands in for ChaCha20Rng::from_seed (examples/nqueens/src/main.rs:39,66) -- the random
+ * STREAM is not reference-identical (rand/rand_chacha are un-vendored), only replayable. */
+void cs_philox4x32_10(uint64_t seed, uint32_t chain, uint32_t purpose, uint64_t counter,
+                      uint32_t out[4]);
+const char* cs_status_string(int32_t status);
+
+/* ------------------------------------------------------------------ n-queens */
+typedef struct cs_nq_handle cs_nq_handle;
+
+typedef struct cs_nq_config {
+    uint32_t n;              /* board size, 1..CS_NQ_MAX_N_SMEM */
+    uint32_t n_chains;       /* independent restart chains held by this handle */
+    uint32_t chain_offset;   /* global id of local chain 0 (Philox stream id; rank sharding) */
+    uint32_t trace_capacity; /* chosen-move log entries kept per chain (0 = no trace) */
+    uint64_t seed;           /* Philox key */
+    int32_t device;          /* CUDA ordinal; -1 = current device */
+    uint32_t neighbourhood;  /* CS_NQ_SWAP or CS_NQ_CHANGE */
+} cs_nq_config;
+
+/* LocalSearch::new, local-search/src/local_search.rs:277-299 (the handle owns what the
+ * struct owns: proposer + score calculator + history, for n_chains chains at once). */
+int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out);
+int32_t cs_nq_destroy(cs_nq_handle* h);
+/* NUL-terminated, owned by the handle, valid until the next call on it. */
+const char* cs_nq_last_error(const cs_nq_handle* h);
+/* Run this handle's kernels on a caller-provided cudaStream_t (NULL = default stream). */
+int32_t cs_nq_set_stream(cs_nq_handle* h, void* cuda_stream);
+
+/* InitialSolutionGenerator::generate_initial_solution, examples/nqueens/src/lib.rs:152-161:
+ * every chain := Fisher-Yates permutation of 0..n-1 from Philox (seed, chain_offset+k, INIT). */
+int32_t cs_nq_init_random(cs_nq_handle* h);
+/* Load `count` solutions (row-major int64 [count][n], values 0..n-1, any multiset -- change
+ * moves and the perturbation legally break the permutation, lib.rs:228,311-312). */
+int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first_chain, uint32_t count,
+                         const int64_t* rows);
+int32_t cs_nq_get_chains(cs_nq_handle* h, uint32_t first_chain, uint32_t count, int64_t* rows);
+/* current score of every chain (maintained by delta, written by step/local_search/set) */
+int32_t cs_nq_get_scores(cs_nq_handle* h, int64_t* scores /* [n_chains] */);
+int32_t cs_nq_get_status(cs_nq_handle* h, uint32_t* status /* [n_chains] */);
+
+/* SolutionScoreCalculator::get_scored_solution, examples/nqueens/src/lib.rs:126-140.
+ * Device FULL re-score by the O(n^2) pair test of get_col_scores (:74-87) -- deliberately
+ * not the counter formulation, so it cross-checks the delta path. */
+int32_t cs_nq_score_full(cs_nq_handle* h, uint32_t chain, int64_t* score);
+
+/* Parity hook: exact score delta of explicit moves against chain's current state, computed
+ * from the diagonal/row occupancy counters.  Identity moves (candidate == current, filtered
+ * by the tabu set, local_search.rs:155-199,319) report INT64_MAX. */
+int32_t cs_nq_eval_moves(cs_nq_handle* h, uint32_t chain, uint32_t kind, const cs_move* moves,
+                         uint64_t n_moves, int64_t* delta);
+/* MoveProposer::iter_local_moves (local_search.rs:85-89; nqueens lib.rs:173-256), full
+ * neighbourhood of the handle's kind in device enumeration order, identity moves skipped.
+ * Writes up to cap moves; *n_out = total count. */
+int32_t cs_nq_enumerate(cs_nq_handle* h, uint32_t chain, cs_move* moves, uint64_t cap,
+                        uint64_t* n_out);
+/* Debug/parity: run the PRODUCTION neighbourhood scan on one chain and write every
+ * candidate's delta in enumeration order (swap: i<j row-major, n(n-1)/2 entries; change:
+ * (c,v) row-major, n*n entries); identity -> INT64_MAX. */
+int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, int64_t* delta,
+                                   uint64_t cap, uint64_t* n_out);
+
+/* The hot path: for every chain, n_steps times: enumerate the full neighbourhood,
+ * delta-score every candidate, argmin by (delta, a, b), accept unconditionally
+ * (local_search.rs:315-335 with window = whole neighbourhood).  A chain stops early when its
+ * score is_best or its neighbourhood is empty.  stats may be NULL. */
+int32_t cs_nq_step(cs_nq_handle* h, uint32_t n_steps, cs_step_stats* stats);
+
+/* LocalSearch::execute, local-search/src/local_search.rs:301-342, on every chain from its
+ * current state: bounded non-improving acceptance, best_solution bookkeeping (:326-328),
+ * max_iterations.  Afterwards get_chains = last `current`, get_best_chains = returned best. */
+int32_t cs_nq_local_search(cs_nq_handle* h, uint64_t allow_no_improvement_for,
+                           uint64_t max_iterations, cs_step_stats* stats);
+int32_t cs_nq_get_best_chains(cs_nq_handle* h, uint32_t first_chain, uint32_t count,
+                              int64_t* rows, int64_t* best_scores);
+/* Single-solution convenience with execute()'s exact shape: start -> best (+ score). */
+int32_t cs_nq_local_search_one(cs_nq_handle* h, const int64_t* start,
+                               uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                               int64_t* best, int64_t* best_score);
+
+/* Chosen-move log of a chain since the last set/init (for CPU replay through the reference
+ * scorer).  score_after[k] is the chain's score after move k.  *n_out = moves logged in total
+ * (may exceed cap/trace_capacity; only the first trace_capacity are kept). */
+int32_t cs_nq_get_trace(cs_nq_handle* h, uint32_t chain, cs_move* moves, int64_t* score_after,
+                        uint64_t cap, uint64_t* n_out);
+/* Best current solution over this handle's chains. Any out pointer may be NULL. */
+int32_t cs_nq_best(cs_nq_handle* h, int64_t* rows, int64_t* score, uint32_t* chain);
+/* Device pointer to the packed best key of this handle ((score << 32) | global chain id,
+ * int64, refreshed by step/local_search) so a host collective (NCCL min-allreduce) can run
+ * on it without a host round trip. */
+int32_t cs_nq_best_key_device_ptr(cs_nq_handle* h, void** dptr);
+/* Overwrite one chain with a solution (elite broadcast target). */
+int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain, const void* d_rows_u16);
+/* Device pointer to chain's rows (uint16 [n], padded stride available via *stride_elems). */
+int32_t cs_nq_chain_device_ptr(cs_nq_handle* h, uint32_t chain, void** dptr,
+                               uint32_t* stride_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

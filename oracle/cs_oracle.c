@@ -1,0 +1,514 @@
+/*
+ * cs_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY).  See cs_oracle.h for the rules.
+ *
+ * Restates, in plain C, the reference's algorithm for the move-evaluation path:
+ *   examples/nqueens/src/lib.rs            (score definition, initial solution)
+ *   examples/employee-scheduling/src/lib.rs (score definition)
+ *   local-search/src/local_search.rs        (LocalSearch::execute, tabu quirk)
+ * Deliberately the SLOW formulation the reference uses (clone + full re-score per
+ * candidate): it is the independent check for the GPU's counter/delta formulation.
+ */
+#include "cs_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ Philox4x32-10 */
+/* Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3" (SC'11). */
+static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0];
+    const uint32_t n2 = hi0 ^ c[3] ^ k[1];
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k[2] = {key[0], key[1]};
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k);
+        k[0] += 0x9E3779B9u;
+        k[1] += 0xBB67AE85u;
+    }
+    memcpy(out, c, sizeof(c));
+}
+
+void orc_philox_stream(uint64_t seed, uint32_t chain, uint32_t purpose, uint64_t counter,
+                       uint32_t out[4]) {
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const uint32_t ctr[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), chain, purpose};
+    orc_philox4x32_10(ctr, key, out);
+}
+
+uint32_t orc_philox_draw(uint64_t seed, uint32_t chain, uint32_t purpose, uint64_t t) {
+    uint32_t o[4];
+    orc_philox_stream(seed, chain, purpose, t >> 2, o);
+    return o[t & 3];
+}
+
+/* ------------------------------------------------------------------ n-queens */
+
+/* examples/nqueens/src/lib.rs:74-87 */
+void orc_nq_col_scores(const int64_t* rows, int64_t n, int64_t* out) {
+    for (int64_t c = 0; c < n; ++c) out[c] = 0;
+    for (int64_t col1 = 0; col1 < n; ++col1) {
+        const int64_t row1 = rows[col1];
+        for (int64_t col2 = col1 + 1; col2 < n; ++col2) {
+            const int64_t row_diff = rows[col2] - row1;
+            const int64_t column_diff = col2 - col1;
+            const int64_t ar = row_diff < 0 ? -row_diff : row_diff;
+            if (row_diff == 0 || ar == column_diff) { /* :80 */
+                out[col1] += 1;
+                out[col2] += 1;
+            }
+        }
+    }
+}
+
+/* examples/nqueens/src/lib.rs:130-139 : score = sum of per-column conflict counts.
+ * Same pair loop as above, accumulated directly (every conflicting pair adds 2). */
+int64_t orc_nq_score(const int64_t* rows, int64_t n) {
+    int64_t pairs = 0;
+    for (int64_t col1 = 0; col1 < n; ++col1) {
+        const int64_t row1 = rows[col1];
+        int64_t local = 0;
+        for (int64_t col2 = col1 + 1; col2 < n; ++col2) {
+            const int64_t row_diff = rows[col2] - row1;
+            const int64_t column_diff = col2 - col1;
+            const int64_t ar = row_diff < 0 ? -row_diff : row_diff;
+            local += (row_diff == 0) | (ar == column_diff);
+        }
+        pairs += local;
+    }
+    return 2 * pairs;
+}
+
+/* examples/nqueens/src/lib.rs:156-160 */
+void orc_nq_init_perm(uint64_t seed, uint32_t chain, int64_t n, int64_t* rows) {
+    for (int64_t i = 0; i < n; ++i) rows[i] = i;
+    uint64_t t = 0;
+    for (int64_t k = n - 1; k >= 1; --k, ++t) {
+        const uint32_t u = orc_philox_draw(seed, chain, 0u, t);
+        const int64_t idx = (int64_t)(((uint64_t)u * (uint64_t)(k + 1)) >> 32);
+        const int64_t tmp = rows[k];
+        rows[k] = rows[idx];
+        rows[idx] = tmp;
+    }
+}
+
+static int nq_apply(int64_t* cand, int kind, int64_t a, int64_t b) {
+    /* returns 0 when the candidate equals the current solution (tabu == {current},
+     * local_search.rs:155-199 quirk + :319) */
+    if (kind == ORC_NQ_SWAP) {
+        if (cand[a] == cand[b]) return 0;
+        const int64_t t = cand[a];
+        cand[a] = cand[b];
+        cand[b] = t;
+        return 1;
+    }
+    if (cand[a] == b) return 0; /* examples/nqueens/src/lib.rs:227-229: rows[col] = value */
+    cand[a] = b;
+    return 1;
+}
+
+void orc_nq_eval_moves(const int64_t* rows, int64_t n, int kind, const int64_t* a,
+                       const int64_t* b, int64_t n_moves, int64_t* delta) {
+    int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    const int64_t cur = orc_nq_score(rows, n);
+    for (int64_t k = 0; k < n_moves; ++k) {
+        memcpy(cand, rows, sizeof(int64_t) * (size_t)n); /* clone, local_search.rs:315-322 */
+        if (!nq_apply(cand, kind, a[k], b[k])) {
+            delta[k] = INT64_MAX;
+            continue;
+        }
+        delta[k] = orc_nq_score(cand, n) - cur;
+    }
+    free(cand);
+}
+
+int64_t orc_nq_neighbourhood_deltas(const int64_t* rows, int64_t n, int kind, int64_t* delta) {
+    int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    const int64_t cur = orc_nq_score(rows, n);
+    int64_t k = 0;
+    for (int64_t x = 0; x < n; ++x) {
+        const int64_t y0 = (kind == ORC_NQ_SWAP) ? x + 1 : 0;
+        for (int64_t y = y0; y < n; ++y, ++k) {
+            memcpy(cand, rows, sizeof(int64_t) * (size_t)n);
+            if (!nq_apply(cand, kind, x, y)) {
+                delta[k] = INT64_MAX;
+                continue;
+            }
+            delta[k] = orc_nq_score(cand, n) - cur;
+        }
+    }
+    free(cand);
+    return k;
+}
+
+static int lex_less(const int64_t* x, const int64_t* y, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (x[i] != y[i]) return x[i] < y[i];
+    }
+    return 0;
+}
+
+/* local-search/src/local_search.rs:301-342 */
+int64_t orc_nq_local_search(int64_t* rows, int64_t n, int kind, int tie,
+                            uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                            uint64_t window_size, int64_t* best_score, int64_t* current_out,
+                            int64_t* current_score_out, int64_t* trace_a, int64_t* trace_b,
+                            int64_t* trace_score, int64_t cap) {
+    const size_t bytes = sizeof(int64_t) * (size_t)(n > 0 ? n : 1);
+    int64_t* current = (int64_t*)malloc(bytes);
+    int64_t* best = (int64_t*)malloc(bytes);
+    int64_t* cand = (int64_t*)malloc(bytes);
+    int64_t* nb = (int64_t*)malloc(bytes);
+    memcpy(current, rows, bytes);
+    int64_t current_score = orc_nq_score(current, n); /* :306 */
+    memcpy(best, current, bytes);                      /* :307 */
+    int64_t bscore = current_score;
+    uint64_t no_improvement_for = 0;
+    int64_t steps = 0;
+    for (uint64_t it = 0; it < max_iterations; ++it) { /* :309 */
+        /* :310 seen_solution => tabu == {current} (age test inverted, :182-195) */
+        if (current_score == 0) { /* :311-314 returns current_solution */
+            memcpy(best, current, bytes);
+            bscore = current_score;
+            break;
+        }
+        int have = 0;
+        int64_t nb_score = 0, nb_a = -1, nb_b = -1;
+        uint64_t taken = 0;
+        int stop = 0;
+        for (int64_t x = 0; x < n && !stop; ++x) { /* :315-322 */
+            const int64_t y0 = (kind == ORC_NQ_SWAP) ? x + 1 : 0;
+            for (int64_t y = y0; y < n; ++y) {
+                if (window_size && taken >= window_size) { /* .take(window) :321 */
+                    stop = 1;
+                    break;
+                }
+                memcpy(cand, current, bytes);
+                if (!nq_apply(cand, kind, x, y)) continue; /* tabu filter :319 */
+                const int64_t s = orc_nq_score(cand, n);   /* :320 */
+                ++taken;
+                int better;
+                if (!have) better = 1;
+                else if (s != nb_score) better = s < nb_score;
+                else better = (tie == ORC_TIE_REFERENCE) ? lex_less(cand, nb, n) : 0;
+                if (better) { /* sort() then first(), :323-325 */
+                    have = 1;
+                    nb_score = s;
+                    nb_a = x;
+                    nb_b = y;
+                    memcpy(nb, cand, bytes);
+                }
+            }
+        }
+        if (!have) break; /* :336-338 */
+        if (nb_score < current_score) { /* :326-328 */
+            memcpy(best, nb, bytes);
+            bscore = nb_score;
+            no_improvement_for = 0;
+        } else { /* :329-334 */
+            no_improvement_for += 1;
+            if (no_improvement_for >= allow_no_improvement_for) break;
+        }
+        memcpy(current, nb, bytes); /* :335 */
+        current_score = nb_score;
+        if (steps < cap) {
+            if (trace_a) trace_a[steps] = nb_a;
+            if (trace_b) trace_b[steps] = nb_b;
+            if (trace_score) trace_score[steps] = nb_score;
+        }
+        ++steps;
+    }
+    memcpy(rows, best, bytes); /* :341 */
+    if (best_score) *best_score = bscore;
+    if (current_out) memcpy(current_out, current, bytes);
+    if (current_score_out) *current_score_out = current_score;
+    free(current);
+    free(best);
+    free(cand);
+    free(nb);
+    return steps;
+}
+
+int64_t orc_nq_baseline_sample(const int64_t* rows, int64_t n, const int64_t* a,
+                               const int64_t* b, int64_t n_moves, int threads,
+                               int64_t* checksum) {
+    int64_t sum = 0;
+    const int64_t cur = orc_nq_score(rows, n);
+#pragma omp parallel num_threads(threads) reduction(+ : sum)
+    {
+        int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t k = 0; k < n_moves; ++k) {
+            memcpy(cand, rows, sizeof(int64_t) * (size_t)n);
+            if (nq_apply(cand, ORC_NQ_SWAP, a[k], b[k])) sum += orc_nq_score(cand, n) - cur;
+        }
+        free(cand);
+    }
+    if (checksum) *checksum = sum;
+    return n_moves;
+}
+
+/* ------------------------------------------------------------------ employee scheduling */
+
+/* Proleptic Gregorian civil-date arithmetic (what chrono's NaiveDate does). */
+int64_t orc_days_from_civil(int64_t y, int m, int d) {
+    y -= m <= 2;
+    const int64_t era = (y >= 0 ? y : y - 399) / 400;
+    const int64_t yoe = y - era * 400;
+    const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+    const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + doe - 719468;
+}
+
+int orc_weekday_from_days(int64_t z) {
+    /* 1970-01-01 was a Thursday (=3 with Monday=0). */
+    int64_t w = (z + 3) % 7;
+    if (w < 0) w += 7;
+    return (int)w;
+}
+
+static inline int es_is_weekend(int start_weekday, int64_t i) {
+    const int w = (int)((start_weekday + i) % 7);
+    return w == 5 || w == 6; /* lib.rs:220-222 */
+}
+
+/* count distinct ids in window with multiplicity > limit (itertools counts(), lib.rs:319-326) */
+static int64_t es_window_violations(const int64_t* w, int64_t len, int64_t limit) {
+    int64_t v = 0;
+    for (int64_t p = 0; p < len; ++p) {
+        int first = 1;
+        for (int64_t q = 0; q < p; ++q)
+            if (w[q] == w[p]) { first = 0; break; }
+        if (!first) continue;
+        int64_t c = 0;
+        for (int64_t q = p; q < len; ++q) c += (w[q] == w[p]);
+        if (c > limit) ++v;
+    }
+    return v;
+}
+
+int orc_es_score_terms(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                       const int64_t* hol_day, int64_t n_hol, int64_t out[8]) {
+    for (int k = 0; k < 8; ++k) out[k] = 0;
+    /* H1 holidays, lib.rs:273-280 */
+    for (int64_t k = 0; k < n_hol; ++k) {
+        if (hol_day[k] < 0 || hol_day[k] >= D) return -1; /* unwrap() on None, :275 */
+        if (a[hol_day[k]] == hol_emp[k]) out[0] += 1;
+    }
+    /* H2 consecutive days, lib.rs:286-292 */
+    for (int64_t i = 0; i + 2 <= D; ++i)
+        if (a[i] == a[i + 1]) out[1] += 1;
+    /* H3 consecutive weekends, lib.rs:295-315 */
+    for (int64_t i = 0; i + 9 <= D; ++i) {
+        if (!(es_is_weekend(start_weekday, i) && es_is_weekend(start_weekday, i + 1))) continue;
+        if (a[i] == a[i + 7]) out[2] += 1;
+        if (a[i] == a[i + 8]) out[2] += 1;
+        if (a[i + 1] == a[i + 7]) out[2] += 1;
+        if (a[i + 1] == a[i + 8]) out[2] += 1;
+    }
+    /* H4 no more than 3 per 14 days, lib.rs:318-327 */
+    for (int64_t i = 0; i + 14 <= D; ++i) out[3] += es_window_violations(a + i, 14, 3);
+    /* S1 no more than 2 per 7 days, lib.rs:330-339 */
+    for (int64_t i = 0; i + 7 <= D; ++i) out[4] += es_window_violations(a + i, 7, 2);
+    /* S2 weekday affinity, lib.rs:194-218: per weekday Mon..Fri with >= 2 distinct
+     * employees, add the minimum per-employee count. */
+    for (int wd = 0; wd < 5; ++wd) {
+        int64_t distinct = 0, minc = INT64_MAX;
+        for (int64_t i = 0; i < D; ++i) {
+            if ((start_weekday + i) % 7 != wd) continue;
+            int first = 1;
+            for (int64_t q = 0; q < i; ++q)
+                if ((start_weekday + q) % 7 == wd && a[q] == a[i]) { first = 0; break; }
+            if (!first) continue;
+            int64_t c = 0;
+            for (int64_t q = i; q < D; ++q)
+                if ((start_weekday + q) % 7 == wd && a[q] == a[i]) ++c;
+            ++distinct;
+            if (c < minc) minc = c;
+        }
+        if (distinct >= 2) out[5] += minc; /* len()<=1 skipped :206; MinMax => += min :212-214 */
+    }
+    /* S3 / S4 spreads over employees present at least once, lib.rs:345-365 */
+    int64_t present = 0, mind = INT64_MAX, maxd = INT64_MIN, minw = INT64_MAX, maxw = INT64_MIN;
+    for (int64_t i = 0; i < D; ++i) {
+        int first = 1;
+        for (int64_t q = 0; q < i; ++q)
+            if (a[q] == a[i]) { first = 0; break; }
+        if (!first) continue;
+        int64_t days = 0, wk = 0;
+        for (int64_t q = i; q < D; ++q)
+            if (a[q] == a[i]) {
+                ++days;
+                wk += es_is_weekend(start_weekday, q);
+            }
+        ++present;
+        if (days < mind) mind = days;
+        if (days > maxd) maxd = days;
+        if (wk < minw) minw = wk;
+        if (wk > maxw) maxw = wk;
+    }
+    if (present >= 2) { /* MinMaxResult::MinMax only for >= 2 elements :349,:363 */
+        out[6] = maxd - mind;
+        out[7] = maxw - minw;
+    }
+    return 0;
+}
+
+int orc_es_score(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                 const int64_t* hol_day, int64_t n_hol, int64_t* hard, int64_t* soft) {
+    int64_t t[8];
+    const int rc = orc_es_score_terms(a, D, start_weekday, hol_emp, hol_day, n_hol, t);
+    if (rc) return rc;
+    *hard = t[0] + t[1] + t[2] + t[3];
+    *soft = t[4] + t[5] + t[6] + t[7];
+    return 0;
+}
+
+static int es_apply(int64_t* cand, const int64_t* employees, int kind, int64_t x, int64_t y) {
+    if (kind == ORC_ES_CHANGE) { /* lib.rs:466-470 */
+        if (cand[x] == employees[y]) return 0;
+        cand[x] = employees[y];
+        return 1;
+    }
+    if (cand[x] == cand[y]) return 0; /* lib.rs:471-478 */
+    const int64_t t = cand[x];
+    cand[x] = cand[y];
+    cand[y] = t;
+    return 1;
+}
+
+int orc_es_eval_moves(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                      const int64_t* hol_day, int64_t n_hol, const int64_t* employees,
+                      int64_t E, int kind, const int64_t* x, const int64_t* y, int64_t n_moves,
+                      int64_t* dhard, int64_t* dsoft) {
+    (void)E;
+    int64_t h0, s0;
+    if (orc_es_score(a, D, start_weekday, hol_emp, hol_day, n_hol, &h0, &s0)) return -1;
+    int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(D > 0 ? D : 1));
+    for (int64_t k = 0; k < n_moves; ++k) {
+        memcpy(cand, a, sizeof(int64_t) * (size_t)D);
+        if (!es_apply(cand, employees, kind, x[k], y[k])) {
+            dhard[k] = INT64_MAX;
+            dsoft[k] = INT64_MAX;
+            continue;
+        }
+        int64_t h, s;
+        orc_es_score(cand, D, start_weekday, hol_emp, hol_day, n_hol, &h, &s);
+        dhard[k] = h - h0;
+        dsoft[k] = s - s0;
+    }
+    free(cand);
+    return 0;
+}
+
+int64_t orc_es_local_search(int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                            const int64_t* hol_day, int64_t n_hol, const int64_t* employees,
+                            int64_t E, uint64_t allow_no_improvement_for,
+                            uint64_t max_iterations, int64_t* best_hard, int64_t* best_soft,
+                            int64_t* current_out, int64_t* trace_kind, int64_t* trace_x,
+                            int64_t* trace_y, int64_t* trace_hard, int64_t* trace_soft,
+                            int64_t cap) {
+    const size_t bytes = sizeof(int64_t) * (size_t)(D > 0 ? D : 1);
+    int64_t* current = (int64_t*)malloc(bytes);
+    int64_t* best = (int64_t*)malloc(bytes);
+    int64_t* cand = (int64_t*)malloc(bytes);
+    int64_t* nb = (int64_t*)malloc(bytes);
+    memcpy(current, a, bytes);
+    int64_t ch, cs;
+    orc_es_score(current, D, start_weekday, hol_emp, hol_day, n_hol, &ch, &cs);
+    memcpy(best, current, bytes);
+    int64_t bh = ch, bs = cs;
+    uint64_t no_improvement_for = 0;
+    int64_t steps = 0;
+    for (uint64_t it = 0; it < max_iterations; ++it) {
+        if (ch == 0 && cs == 0) { /* is_best lib.rs:245-249; local_search.rs:311-314 */
+            memcpy(best, current, bytes);
+            bh = ch;
+            bs = cs;
+            break;
+        }
+        int have = 0;
+        int64_t nh = 0, ns = 0, nk = 0, nx = 0, ny = 0;
+        for (int kind = 0; kind < 2; ++kind) {
+            for (int64_t x = 0; x < D; ++x) {
+                const int64_t y0 = (kind == ORC_ES_SWAP) ? x + 1 : 0;
+                const int64_t y1 = (kind == ORC_ES_SWAP) ? D : E;
+                for (int64_t y = y0; y < y1; ++y) {
+                    memcpy(cand, current, bytes);
+                    if (!es_apply(cand, employees, kind, x, y)) continue;
+                    int64_t h, s;
+                    orc_es_score(cand, D, start_weekday, hol_emp, hol_day, n_hol, &h, &s);
+                    if (!have || h < nh || (h == nh && s < ns)) {
+                        have = 1;
+                        nh = h; ns = s; nk = kind; nx = x; ny = y;
+                        memcpy(nb, cand, bytes);
+                    }
+                }
+            }
+        }
+        if (!have) break;
+        if (nh < ch || (nh == ch && ns < cs)) {
+            memcpy(best, nb, bytes);
+            bh = nh;
+            bs = ns;
+            no_improvement_for = 0;
+        } else {
+            no_improvement_for += 1;
+            if (no_improvement_for >= allow_no_improvement_for) break;
+        }
+        memcpy(current, nb, bytes);
+        ch = nh;
+        cs = ns;
+        if (steps < cap) {
+            if (trace_kind) trace_kind[steps] = nk;
+            if (trace_x) trace_x[steps] = nx;
+            if (trace_y) trace_y[steps] = ny;
+            if (trace_hard) trace_hard[steps] = nh;
+            if (trace_soft) trace_soft[steps] = ns;
+        }
+        ++steps;
+    }
+    memcpy(a, best, bytes);
+    if (best_hard) *best_hard = bh;
+    if (best_soft) *best_soft = bs;
+    if (current_out) memcpy(current_out, current, bytes);
+    free(current);
+    free(best);
+    free(cand);
+    free(nb);
+    return steps;
+}
+
+int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
+                               const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                               const int64_t* employees, int64_t E, int kind, const int64_t* x,
+                               const int64_t* y, int64_t n_moves, int threads,
+                               int64_t* checksum) {
+    (void)E;
+    int64_t sum = 0;
+    int64_t h0, s0;
+    if (orc_es_score(a, D, start_weekday, hol_emp, hol_day, n_hol, &h0, &s0)) return -1;
+#pragma omp parallel num_threads(threads) reduction(+ : sum)
+    {
+        int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(D > 0 ? D : 1));
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < n_moves; ++k) {
+            memcpy(cand, a, sizeof(int64_t) * (size_t)D);
+            if (es_apply(cand, employees, kind, x[k], y[k])) {
+                int64_t h, s;
+                orc_es_score(cand, D, start_weekday, hol_emp, hol_day, n_hol, &h, &s);
+                sum += (h - h0) * 1000 + (s - s0);
+            }
+        }
+        free(cand);
+    }
+    if (checksum) *checksum = sum;
+    return n_moves;
+}

@@ -1,0 +1,223 @@
+"""ctypes loader + numpy wrappers for oracle/libcs_oracle.so.
+
+TEST INFRASTRUCTURE ONLY: the CPU restatement of the reference's algorithm
+(oracle/cs_oracle.c cites the reference file:line for each function).  The product
+package (constraint_solver_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcs_oracle.so")
+
+I64 = C.c_int64
+U64 = C.c_uint64
+P64 = C.POINTER(C.c_int64)
+INT64_MAX = np.iinfo(np.int64).max
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(
+        os.path.join(_HERE, "cs_oracle.c")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_nq_score.restype = I64
+        _lib.orc_nq_neighbourhood_deltas.restype = I64
+        _lib.orc_nq_local_search.restype = I64
+        _lib.orc_nq_baseline_sample.restype = I64
+        _lib.orc_es_local_search.restype = I64
+        _lib.orc_es_baseline_sample.restype = I64
+        _lib.orc_days_from_civil.restype = I64
+        _lib.orc_philox_draw.restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(P64) if a is not None else None
+
+
+def _i64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int64))
+
+
+# ---------------------------------------------------------------- philox
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in ctr])
+    k = (C.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return [int(x) for x in o]
+
+
+def philox_stream(seed, chain, purpose, counter):
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox_stream(U64(seed), C.c_uint32(chain), C.c_uint32(purpose), U64(counter), o)
+    return [int(x) for x in o]
+
+
+# ---------------------------------------------------------------- n-queens
+def nq_col_scores(rows):
+    r = _i64(rows)
+    out = np.zeros(len(r), dtype=np.int64)
+    lib().orc_nq_col_scores(_p(r), I64(len(r)), _p(out))
+    return out
+
+
+def nq_score(rows) -> int:
+    r = _i64(rows)
+    return int(lib().orc_nq_score(_p(r), I64(len(r))))
+
+
+def nq_init_perm(seed, chain, n):
+    out = np.zeros(n, dtype=np.int64)
+    lib().orc_nq_init_perm(U64(seed), C.c_uint32(chain), I64(n), _p(out))
+    return out
+
+
+SWAP, CHANGE = 0, 1
+TIE_MOVE_ORDER, TIE_REFERENCE = 0, 1
+
+
+def nq_neighbourhood_deltas(rows, kind=SWAP):
+    r = _i64(rows)
+    n = len(r)
+    cnt = n * (n - 1) // 2 if kind == SWAP else n * n
+    out = np.zeros(max(cnt, 1), dtype=np.int64)
+    k = lib().orc_nq_neighbourhood_deltas(_p(r), I64(n), C.c_int(kind), _p(out))
+    assert k == cnt
+    return out[:cnt]
+
+
+def nq_eval_moves(rows, a, b, kind=SWAP):
+    r, a, b = _i64(rows), _i64(a), _i64(b)
+    out = np.zeros(max(len(a), 1), dtype=np.int64)
+    lib().orc_nq_eval_moves(_p(r), I64(len(r)), C.c_int(kind), _p(a), _p(b), I64(len(a)), _p(out))
+    return out[: len(a)]
+
+
+def nq_local_search(rows, kind=SWAP, tie=TIE_MOVE_ORDER, allow_no_improvement_for=5,
+                    max_iterations=10_000, window_size=0, trace_cap=0):
+    """LocalSearch::execute restated (local_search.rs:301-342). Returns a dict."""
+    r = _i64(rows).copy()
+    n = len(r)
+    cur = np.zeros(max(n, 1), dtype=np.int64)
+    best_score, cur_score = I64(0), I64(0)
+    ta = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    tb = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    ts = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    steps = lib().orc_nq_local_search(
+        _p(r), I64(n), C.c_int(kind), C.c_int(tie), U64(allow_no_improvement_for),
+        U64(max_iterations), U64(window_size), C.byref(best_score), _p(cur),
+        C.byref(cur_score), _p(ta), _p(tb), _p(ts), I64(trace_cap))
+    k = min(int(steps), trace_cap)
+    return dict(best=r, best_score=int(best_score.value), current=cur[:n],
+                current_score=int(cur_score.value), steps=int(steps),
+                trace_a=ta[:k], trace_b=tb[:k], trace_score=ts[:k])
+
+
+def nq_baseline_sample(rows, a, b, threads):
+    r, a, b = _i64(rows), _i64(a), _i64(b)
+    chk = I64(0)
+    k = lib().orc_nq_baseline_sample(_p(r), I64(len(r)), _p(a), _p(b), I64(len(a)),
+                                     C.c_int(threads), C.byref(chk))
+    return int(k), int(chk.value)
+
+
+# ---------------------------------------------------------------- employee scheduling
+def days_from_civil(y, m, d) -> int:
+    return int(lib().orc_days_from_civil(I64(y), C.c_int(m), C.c_int(d)))
+
+
+def weekday_from_days(z) -> int:
+    return int(lib().orc_weekday_from_days(I64(z)))
+
+
+def weekday(y, m, d) -> int:
+    return weekday_from_days(days_from_civil(y, m, d))
+
+
+def _hol(holidays):
+    if holidays is None or len(holidays) == 0:
+        return _i64([]), _i64([])
+    h = _i64(holidays).reshape(-1, 2)
+    return np.ascontiguousarray(h[:, 0]), np.ascontiguousarray(h[:, 1])
+
+
+def es_score_terms(a, start_weekday=0, holidays=None):
+    """holidays: iterable of (employee_id, day_index). Returns int64[8] = H1..H4,S1..S4."""
+    a = _i64(a)
+    he, hd = _hol(holidays)
+    out = np.zeros(8, dtype=np.int64)
+    rc = lib().orc_es_score_terms(_p(a), I64(len(a)), C.c_int(start_weekday), _p(he), _p(hd),
+                                  I64(len(he)), _p(out))
+    if rc:
+        raise ValueError("holiday outside the scored range (the reference panics: lib.rs:275)")
+    return out
+
+
+def es_score(a, start_weekday=0, holidays=None):
+    t = es_score_terms(a, start_weekday, holidays)
+    return int(t[:4].sum()), int(t[4:].sum())
+
+
+ES_CHANGE, ES_SWAP = 0, 1
+
+
+def es_eval_moves(a, employees, x, y, kind, start_weekday=0, holidays=None):
+    a, employees, x, y = _i64(a), _i64(employees), _i64(x), _i64(y)
+    he, hd = _hol(holidays)
+    dh = np.zeros(max(len(x), 1), dtype=np.int64)
+    ds = np.zeros(max(len(x), 1), dtype=np.int64)
+    rc = lib().orc_es_eval_moves(_p(a), I64(len(a)), C.c_int(start_weekday), _p(he), _p(hd),
+                                 I64(len(he)), _p(employees), I64(len(employees)),
+                                 C.c_int(kind), _p(x), _p(y), I64(len(x)), _p(dh), _p(ds))
+    if rc:
+        raise ValueError("holiday outside the scored range")
+    return dh[: len(x)], ds[: len(x)]
+
+
+def es_local_search(a, employees, start_weekday=0, holidays=None,
+                    allow_no_improvement_for=20, max_iterations=1000, trace_cap=0):
+    a = _i64(a).copy()
+    employees = _i64(employees)
+    he, hd = _hol(holidays)
+    D = len(a)
+    cur = np.zeros(max(D, 1), dtype=np.int64)
+    bh, bs = I64(0), I64(0)
+    tr = [np.zeros(max(trace_cap, 1), dtype=np.int64) for _ in range(5)]
+    steps = lib().orc_es_local_search(
+        _p(a), I64(D), C.c_int(start_weekday), _p(he), _p(hd), I64(len(he)), _p(employees),
+        I64(len(employees)), U64(allow_no_improvement_for), U64(max_iterations),
+        C.byref(bh), C.byref(bs), _p(cur), _p(tr[0]), _p(tr[1]), _p(tr[2]), _p(tr[3]),
+        _p(tr[4]), I64(trace_cap))
+    k = min(int(steps), trace_cap)
+    return dict(best=a, best_hard=int(bh.value), best_soft=int(bs.value), current=cur[:D],
+                steps=int(steps), trace_kind=tr[0][:k], trace_x=tr[1][:k], trace_y=tr[2][:k],
+                trace_hard=tr[3][:k], trace_soft=tr[4][:k])
+
+
+def es_baseline_sample(a, employees, x, y, kind, threads, start_weekday=0, holidays=None):
+    a, employees, x, y = _i64(a), _i64(employees), _i64(x), _i64(y)
+    he, hd = _hol(holidays)
+    chk = I64(0)
+    k = lib().orc_es_baseline_sample(_p(a), I64(len(a)), C.c_int(start_weekday), _p(he),
+                                     _p(hd), I64(len(he)), _p(employees), I64(len(employees)),
+                                     C.c_int(kind), _p(x), _p(y), I64(len(x)),
+                                     C.c_int(threads), C.byref(chk))
+    return int(k), int(chk.value)

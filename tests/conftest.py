@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    # the product .so and the oracle .so are built in-tree by __graft_entry__.build();
+    # build them here too so a bare `pytest` works from a clean checkout
+    so = os.path.join(ROOT, "constraint_solver_b200", "libcs_b200.so")
+    orc = os.path.join(ROOT, "oracle", "libcs_oracle.so")
+    if not (os.path.exists(so) and os.path.exists(orc)):
+        import __graft_entry__ as g
+
+        g.build()

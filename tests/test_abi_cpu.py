@@ -1,0 +1,75 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/cs_b200.h declares
+(no compute calls -- there is no GPU here), and refuses to run without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import constraint_solver_b200 as cs
+from constraint_solver_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    for fn in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not fn.endswith(".h"):
+            continue
+        src = open(os.path.join(ROOT, "include", fn)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names += re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_symbols_all_exported_and_bound():
+    lib = cs.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+        assert name in L.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(L.SIGNATURES) == declared
+
+
+def test_abi_version_and_status_strings():
+    lib = cs.load()
+    assert lib.cs_abi_version() == 1
+    assert b"no CPU fallback" in lib.cs_status_string(L.CS_ERR_NO_DEVICE)
+
+
+def test_host_philox_mirror_matches_oracle():
+    from oracle import oracle as orc
+
+    for (seed, chain, purpose, ctr) in [(0, 0, 0, 0), (42, 7, 1, 123456789012), (2**63 + 5, 2**32 - 1, 3, 2**40)]:
+        assert cs.philox4x32_10(seed, chain, purpose, ctr) == orc.philox_stream(seed, chain, purpose, ctr)
+
+
+def test_invalid_config_rejected_before_touching_a_device():
+    lib = cs.load()
+    h = C.c_void_p()
+    bad = L.CsNqConfig(n=0, n_chains=1, chain_offset=0, trace_capacity=0, seed=1, device=-1, neighbourhood=0)
+    assert lib.cs_nq_create(C.byref(bad), C.byref(h)) == L.CS_ERR_INVALID_ARG
+    big = L.CsNqConfig(n=L.CS_NQ_MAX_N_SMEM + 1, n_chains=1, chain_offset=0, trace_capacity=0, seed=1,
+                       device=-1, neighbourhood=0)
+    assert lib.cs_nq_create(C.byref(big), C.byref(h)) == L.CS_ERR_UNSUPPORTED
+    assert lib.cs_nq_create(None, C.byref(h)) == L.CS_ERR_INVALID_ARG
+    assert lib.cs_nq_destroy(None) == L.CS_ERR_INVALID_ARG
+
+
+def test_no_cpu_fallback_without_device():
+    if cs.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cs.CsError) as e:
+        cs.NQueensChains(8, 1)
+    assert e.value.status == L.CS_ERR_NO_DEVICE
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "constraint_solver_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.lower().replace("mirrored by the oracle", ""), fn

@@ -1,0 +1,143 @@
+"""CPU suite: the oracle against the golden vectors (the reference's own KATs + SURVEY 8c)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def _load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as f:
+        return json.load(f)
+
+
+def test_philox_known_answers(golden_dir):
+    for case in _load(golden_dir, "philox_kat.json"):
+        assert orc.philox4x32_10(case["ctr"], case["key"]) == case["out"]
+
+
+def test_nq_reference_kats(golden_dir):
+    g = _load(golden_dir, "nq_kat.json")
+    for case in g["reference"] + g["derived"]:
+        assert orc.nq_score(case["rows"]) == case["score"]
+        if "col_scores" in case:
+            assert orc.nq_col_scores(case["rows"]).tolist() == case["col_scores"]
+
+
+def test_nq_score_equals_line_counter_closed_form():
+    # sum over lines k(k-1) == the reference pair loop, incl. non-permutations
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 3, 7, 16, 33, 100):
+        for _ in range(20):
+            rows = rng.integers(0, n, size=n)
+            cols = np.arange(n)
+            tot = 0
+            for key in (rows, cols - rows, cols + rows):
+                _, cnt = np.unique(key, return_counts=True)
+                tot += int((cnt * (cnt - 1)).sum())
+            assert tot == orc.nq_score(rows)
+
+
+def test_nq_selection_kats_reference_tiebreak(golden_dir):
+    # best-of-window under the derived Ord (score, solution lexicographic)
+    for case in _load(golden_dir, "nq_kat.json")["selection"]:
+        rows = np.array(case["rows"], dtype=np.int64)
+        n = len(rows)
+        cands = []
+        for c in case["cols"]:
+            for v in range(n):
+                if v == rows[c]:
+                    continue
+                r = rows.copy()
+                r[c] = v
+                cands.append((orc.nq_score(r), tuple(r.tolist())))
+        cands.sort()
+        assert list(cands[0][1]) == case["chosen"] and cands[0][0] == case["score"]
+
+
+def test_nq_init_perm_is_permutation_and_deterministic():
+    a = orc.nq_init_perm(42, 3, 1000)
+    b = orc.nq_init_perm(42, 3, 1000)
+    c = orc.nq_init_perm(42, 4, 1000)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert sorted(a.tolist()) == list(range(1000))
+
+
+def test_nq_local_search_follows_execute_semantics():
+    # local_search.rs:301-342: returns current when is_best; best = last improving neighbour;
+    # identity candidates are the only tabu ones; empty neighbourhood breaks.
+    res = orc.nq_local_search([1, 3, 0, 2], trace_cap=8)
+    assert res["steps"] == 0 and res["best_score"] == 0
+    res = orc.nq_local_search([0, 0, 0, 0], kind=orc.SWAP, trace_cap=8)  # all swaps identity
+    assert res["steps"] == 0 and res["best_score"] == 12
+    rows = orc.nq_init_perm(1, 0, 12)
+    res = orc.nq_local_search(rows, allow_no_improvement_for=3, max_iterations=50, trace_cap=64)
+    r = rows.copy()
+    best_seen, cur = None, orc.nq_score(rows)
+    for (i, j, s) in zip(res["trace_a"], res["trace_b"], res["trace_score"]):
+        r[i], r[j] = r[j], r[i]
+        assert orc.nq_score(r) == s
+        if s < cur:
+            best_seen = (s, r.copy())
+        cur = s
+    if best_seen is not None:
+        assert res["best_score"] == best_seen[0] and np.array_equal(res["best"], best_seen[1])
+    # max_iterations bounds the accepted steps
+    res2 = orc.nq_local_search(rows, allow_no_improvement_for=1000, max_iterations=2, trace_cap=8)
+    assert res2["steps"] <= 2
+
+
+def test_nq_window_and_reference_tiebreak_modes():
+    rows = orc.nq_init_perm(9, 0, 10)
+    full = orc.nq_local_search(rows, kind=orc.CHANGE, tie=orc.TIE_REFERENCE, max_iterations=1,
+                               allow_no_improvement_for=5, trace_cap=4)
+    win = orc.nq_local_search(rows, kind=orc.CHANGE, tie=orc.TIE_REFERENCE, max_iterations=1,
+                              allow_no_improvement_for=5, window_size=7, trace_cap=4)
+    assert full["trace_score"][0] <= win["trace_score"][0]
+    assert win["trace_a"][0] == 0  # first 7 non-identity candidates all live in column 0
+
+
+def test_weekday_arithmetic():
+    assert orc.weekday(2022, 5, 9) == 0  # Monday, examples/employee-scheduling/src/main.rs:11
+    assert orc.weekday(1970, 1, 1) == 3
+    assert orc.weekday(2000, 2, 29) == 1
+    assert orc.days_from_civil(2022, 6, 8) - orc.days_from_civil(2022, 5, 9) == 30
+
+
+def test_es_golden_vectors(golden_dir):
+    g = _load(golden_dir, "es_kat.json")
+    for case in g["cases"]:
+        hard, soft = orc.es_score(case["a"], g["start_weekday"], case["holidays"])
+        assert (hard, soft) == (case["hard"], case["soft"]), case
+        assert orc.es_score_terms(case["a"], g["start_weekday"], case["holidays"]).tolist() == case["terms"]
+
+
+def test_es_holiday_out_of_range_is_an_error():
+    with pytest.raises(ValueError):
+        orc.es_score([0, 1, 2], 0, [(0, 3)])
+
+
+def test_es_phantom_slot_is_not_scored():
+    # date_to_employee has D+1 entries (lib.rs:405-412); scoring reads only the first D
+    a = [i % 7 for i in range(31)]
+    assert orc.es_score(a, 0) == orc.es_score(np.array(a + [3])[:31], 0)
+
+
+def test_es_local_search_trace_replays():
+    rng = np.random.default_rng(5)
+    emp = np.arange(5)
+    a = rng.integers(0, 5, size=16)
+    hol = [(0, 1), (2, 7), (4, 15)]
+    res = orc.es_local_search(a, emp, 0, hol, allow_no_improvement_for=4, max_iterations=12,
+                              trace_cap=32)
+    cur = a.copy()
+    for k, x, y, h, s in zip(res["trace_kind"], res["trace_x"], res["trace_y"],
+                             res["trace_hard"], res["trace_soft"]):
+        if k == orc.ES_CHANGE:
+            cur[x] = emp[y]
+        else:
+            cur[x], cur[y] = cur[y], cur[x]
+        assert orc.es_score(cur, 0, hol) == (h, s)
+    assert np.array_equal(cur, res["current"])
