@@ -63,6 +63,41 @@ class CsNqConfig(C.Structure):
     ]
 
 
+class CsEsConfig(C.Structure):
+    _fields_ = [
+        ("n_days", C.c_uint32),
+        ("n_employees", C.c_uint32),
+        ("start_weekday", C.c_uint32),
+        ("n_chains", C.c_uint32),
+        ("chain_offset", C.c_uint32),
+        ("trace_capacity", C.c_uint32),
+        ("seed", C.c_uint64),
+        ("device", C.c_int32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class CsEsMove(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("a", C.c_uint32), ("b", C.c_uint32)]
+
+
+class CsEsStepStats(C.Structure):
+    _fields_ = [
+        ("moves_scored", C.c_uint64),
+        ("steps_accepted", C.c_uint64),
+        ("best_hard", C.c_int64),
+        ("best_soft", C.c_int64),
+        ("best_chain", C.c_uint32),
+        ("chains_at_best", C.c_uint32),
+        ("chains_feasible", C.c_uint32),
+        ("device_ms", C.c_float),
+        ("kernel_launches", C.c_uint32),
+    ]
+
+
+CS_ES_CHANGE, CS_ES_SWAP = 0, 1
+CS_ES_MAX_DAYS = 64
+
 _P = C.POINTER
 _VP = C.c_void_p
 
@@ -94,6 +129,27 @@ SIGNATURES = {
     "cs_nq_best_key_device_ptr": (C.c_int32, [_VP, _P(_VP)]),
     "cs_nq_set_chain_u16_device": (C.c_int32, [_VP, C.c_uint32, _VP]),
     "cs_nq_chain_device_ptr": (C.c_int32, [_VP, C.c_uint32, _P(_VP), _P(C.c_uint32)]),
+    "cs_es_create": (C.c_int32, [_P(CsEsConfig), _VP, _VP, _VP, C.c_uint64, _P(_VP)]),
+    "cs_es_destroy": (C.c_int32, [_VP]),
+    "cs_es_last_error": (C.c_char_p, [_VP]),
+    "cs_es_set_stream": (C.c_int32, [_VP, _VP]),
+    "cs_es_init_random": (C.c_int32, [_VP]),
+    "cs_es_set_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "cs_es_get_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "cs_es_get_scores": (C.c_int32, [_VP, _VP, _VP]),
+    "cs_es_get_status": (C.c_int32, [_VP, _VP]),
+    "cs_es_score_full": (C.c_int32, [_VP, C.c_uint32, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
+    "cs_es_eval_moves": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _VP, _VP]),
+    "cs_es_enumerate": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
+    "cs_es_neighbourhood_deltas": (C.c_int32, [_VP, C.c_uint32, _VP, _VP, C.c_uint64, _P(C.c_uint64)]),
+    "cs_es_step": (C.c_int32, [_VP, C.c_uint32, _P(CsEsStepStats)]),
+    "cs_es_local_search": (C.c_int32, [_VP, C.c_uint64, C.c_uint64, _P(CsEsStepStats)]),
+    "cs_es_get_best_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
+    "cs_es_local_search_one": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint64, _VP, _P(C.c_int64), _P(C.c_int64)]),
+    "cs_es_get_trace": (C.c_int32, [_VP, C.c_uint32, _VP, _VP, _VP, C.c_uint64, _P(C.c_uint64)]),
+    "cs_es_best": (C.c_int32, [_VP, _VP, _P(C.c_int64), _P(C.c_int64), _P(C.c_uint32)]),
+    "cs_es_best_key_device_ptr": (C.c_int32, [_VP, _P(_VP)]),
+    "cs_es_chain_device_ptr": (C.c_int32, [_VP, C.c_uint32, _P(_VP), _P(C.c_uint32)]),
 }
 
 _lib = None

@@ -669,3 +669,5 @@ extern "C" int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain,
         CU(cudaStreamSynchronize(h->stream));
     });
 }
+
+#include "es_api.cuh"

@@ -1,0 +1,575 @@
+// C ABI for the employee-scheduling plug-in (included by cs_api.cu; shares its helpers).
+#pragma once
+#include <algorithm>
+
+#include "es_kernels.cuh"
+
+struct cs_es_handle {
+    cs_es_config cfg{};
+    int device = 0;
+    int stride = 0;   // D + 1 slots
+    int threads = 128;
+    int grid_cap = 1;
+    size_t smem = 0;
+    EsConst K{};
+    std::vector<int64_t> ids;  // sorted employee ids (BTreeSet order)
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint16_t* d_a = nullptr;
+    uint16_t* d_best_a = nullptr;
+    u64* d_hol = nullptr;
+    EsChainState* d_st = nullptr;
+    EsTraceEntry* d_trace = nullptr;
+    unsigned int* d_work = nullptr;
+    unsigned long long* d_totals = nullptr;
+    EsStats* d_stats = nullptr;
+    EsStats* h_stats = nullptr;
+    unsigned long long* h_totals = nullptr;
+    uint16_t* h_stage = nullptr;  // pinned staging for id <-> index conversion
+    size_t stage_chains = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool scored = false;
+    std::string err;
+};
+
+namespace {
+
+EsParams es_params(cs_es_handle* h, int first, int count) {
+    EsParams p{};
+    p.K = h->K;
+    p.first_chain = first;
+    p.n_chains = count;
+    p.stride = h->stride;
+    p.a = h->d_a;
+    p.best_a = h->d_best_a;
+    p.hol = h->d_hol;
+    p.st = h->d_st;
+    p.trace = h->d_trace;
+    p.trace_cap = (int)h->cfg.trace_capacity;
+    p.work_counter = h->d_work;
+    p.totals = h->d_totals;
+    return p;
+}
+
+void es_free(cs_es_handle* h) {
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_a);
+    cudaFree(h->d_best_a);
+    cudaFree(h->d_hol);
+    cudaFree(h->d_st);
+    cudaFree(h->d_trace);
+    cudaFree(h->d_work);
+    cudaFree(h->d_totals);
+    cudaFree(h->d_stats);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_totals) cudaFreeHost(h->h_totals);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+}
+
+void es_check_range(cs_es_handle* h, uint32_t first, uint32_t count) {
+    REQUIRE(count > 0 && first < h->cfg.n_chains && count <= h->cfg.n_chains - first,
+            "chain range outside [0, n_chains)");
+}
+
+void es_rescore(cs_es_handle* h, int first, int count) {
+    EsParams p = es_params(h, first, count);
+    const int grid = count < h->grid_cap ? count : h->grid_cap;
+    es_rescore_kernel<<<grid, h->threads, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+}
+
+void es_refresh_stats(cs_es_handle* h) {
+    es_stats_kernel<<<1, 1024, 0, h->stream>>>(h->d_st, (int)h->cfg.n_chains, h->cfg.chain_offset,
+                                                h->d_stats);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(EsStats), cudaMemcpyDeviceToHost, h->stream));
+}
+
+void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
+            unsigned long long allow, int ls_mode, cs_es_step_stats* stats) {
+    if (!h->scored) throw StateFail{"chains have no solution yet: call cs_es_init_random or cs_es_set_chains first"};
+    EsParams p = es_params(h, first, count);
+    p.max_steps = max_steps;
+    p.allow_no_improve = allow;
+    p.ls_mode = ls_mode;
+    CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+    CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
+    const int grid = count < h->grid_cap ? count : h->grid_cap;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    es_step_kernel<<<grid, h->threads, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    es_refresh_stats(h);
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (stats) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        stats->moves_scored = h->h_totals[0];
+        stats->steps_accepted = h->h_totals[1];
+        stats->best_hard = h->h_stats->best_hard;
+        stats->best_soft = h->h_stats->best_soft;
+        stats->best_chain = h->h_stats->best_chain;
+        stats->chains_at_best = h->h_stats->chains_at_best;
+        stats->chains_feasible = h->h_stats->chains_feasible;
+        stats->device_ms = ms;
+        stats->kernel_launches = 2;
+    }
+}
+
+int es_index_of(cs_es_handle* h, int64_t id) {
+    auto it = std::lower_bound(h->ids.begin(), h->ids.end(), id);
+    if (it == h->ids.end() || *it != id) return -1;
+    return (int)(it - h->ids.begin());
+}
+
+void es_upload(cs_es_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
+    const size_t stride = h->stride;
+    for (uint32_t done = 0; done < count;) {
+        const uint32_t c = (uint32_t)std::min<size_t>(count - done, h->stage_chains);
+        for (size_t k = 0; k < (size_t)c * stride; ++k) {
+            const int idx = es_index_of(h, rows[(size_t)done * stride + k]);
+            REQUIRE(idx >= 0, "solution names an employee id that is not in the employee table");
+            h->h_stage[k] = (uint16_t)idx;
+        }
+        CU(cudaMemcpyAsync(h->d_a + (size_t)(first + done) * stride, h->h_stage,
+                           (size_t)c * stride * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        done += c;
+    }
+}
+
+void es_download(cs_es_handle* h, const uint16_t* src, uint32_t first, uint32_t count, int64_t* rows) {
+    const size_t stride = h->stride;
+    for (uint32_t done = 0; done < count;) {
+        const uint32_t c = (uint32_t)std::min<size_t>(count - done, h->stage_chains);
+        CU(cudaMemcpyAsync(h->h_stage, src + (size_t)(first + done) * stride,
+                           (size_t)c * stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (size_t k = 0; k < (size_t)c * stride; ++k)
+            rows[(size_t)done * stride + k] = h->ids[h->h_stage[k]];
+        done += c;
+    }
+}
+
+std::vector<EsChainState> es_states(cs_es_handle* h, uint32_t first, uint32_t count) {
+    std::vector<EsChainState> st(count);
+    CU(cudaMemcpyAsync(st.data(), h->d_st + first, count * sizeof(EsChainState),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return st;
+}
+
+}  // namespace
+
+extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee_ids,
+                                const int64_t* hol_emp, const int64_t* hol_day, uint64_t n_hol,
+                                cs_es_handle** out) {
+    if (!cfg || !out || !employee_ids) return CS_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->n_days < 1 || cfg->n_employees < 1 || cfg->n_employees > 65535 || cfg->n_chains < 1 ||
+        cfg->start_weekday > 6)
+        return CS_ERR_INVALID_ARG;
+    if (cfg->n_days > CS_ES_MAX_DAYS) return CS_ERR_UNSUPPORTED;
+    if (n_hol && (!hol_emp || !hol_day)) return CS_ERR_INVALID_ARG;
+    if ((uint64_t)cfg->chain_offset + cfg->n_chains > 0xffffffffull) return CS_ERR_INVALID_ARG;
+    // argument validation that needs no device comes first (the reference would panic)
+    std::vector<int64_t> ids(employee_ids, employee_ids + cfg->n_employees);
+    std::sort(ids.begin(), ids.end());
+    if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) return CS_ERR_INVALID_ARG;
+    for (uint64_t k = 0; k < n_hol; ++k)
+        if (hol_day[k] < 0 || hol_day[k] >= (int64_t)cfg->n_days) return CS_ERR_INVALID_ARG;
+    int ndev = cs_device_count();
+    if (ndev <= 0) return CS_ERR_NO_DEVICE;
+    int dev = cfg->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) return CS_ERR_NO_DEVICE;
+    }
+    if (dev >= ndev) return CS_ERR_INVALID_ARG;
+    cs_es_handle* h = new (std::nothrow) cs_es_handle();
+    if (!h) return CS_ERR_OOM;
+    h->cfg = *cfg;
+    h->device = dev;
+    h->ids = ids;
+    const int32_t rc = guarded(h, [&] {
+        const int D = (int)cfg->n_days, E = (int)cfg->n_employees;
+        h->stride = D + 1;
+        EsConst& K = h->K;
+        K.D = D;
+        K.E = E;
+        K.start_wd = (int)cfg->start_weekday;
+        K.n14 = D >= 14 ? D - 13 : 0;
+        K.n7 = D >= 7 ? D - 6 : 0;
+        K.valid = D == 64 ? ~0ull : ((1ull << D) - 1);
+        K.wkend = 0;
+        K.satf = 0;
+        for (int w = 0; w < 7; ++w) K.wd[w] = 0;
+        for (int d = 0; d < D; ++d) {
+            const int w = (K.start_wd + d) % 7;
+            K.wd[w] |= 1ull << d;
+            if (w >= 5) K.wkend |= 1ull << d;
+            if (w == 5 && d + 9 <= D) K.satf |= 1ull << d;  // windows(9) start, lib.rs:295-302
+        }
+        std::vector<u64> hol(E, 0ull);
+        for (uint64_t k = 0; k < n_hol; ++k) {
+            const int idx = es_index_of(h, hol_emp[k]);
+            if (idx >= 0) hol[idx] |= 1ull << hol_day[k];  // unknown employees never match a day
+        }
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, dev));
+        h->smem = es_smem_bytes(D, E);
+        REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin, "employee table too large for shared memory");
+        const long long moves = (long long)D * E + (long long)D * (D - 1) / 2;
+        h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : moves <= 32768 ? 128 : 256;
+        CU(cudaFuncSetAttribute(es_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CU(cudaFuncSetAttribute(es_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CU(cudaFuncSetAttribute(es_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        int per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel, h->threads, h->smem));
+        if (per_sm < 1) per_sm = 1;
+        h->grid_cap = prop.multiProcessorCount * per_sm;
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+        const size_t nc = cfg->n_chains;
+        CU(cudaMalloc(&h->d_a, nc * h->stride * sizeof(uint16_t)));
+        CU(cudaMalloc(&h->d_best_a, nc * h->stride * sizeof(uint16_t)));
+        CU(cudaMalloc(&h->d_hol, (size_t)E * sizeof(u64)));
+        CU(cudaMalloc(&h->d_st, nc * sizeof(EsChainState)));
+        if (cfg->trace_capacity)
+            CU(cudaMalloc(&h->d_trace, nc * cfg->trace_capacity * sizeof(EsTraceEntry)));
+        CU(cudaMalloc(&h->d_work, sizeof(unsigned int)));
+        CU(cudaMalloc(&h->d_totals, 2 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_stats, sizeof(EsStats)));
+        CU(cudaMallocHost(&h->h_stats, sizeof(EsStats)));
+        CU(cudaMallocHost(&h->h_totals, 2 * sizeof(unsigned long long)));
+        h->stage_chains = std::min<size_t>(nc, std::max<size_t>(1, (size_t)(8u << 20) / (h->stride * 2)));
+        CU(cudaMallocHost(&h->h_stage, h->stage_chains * h->stride * sizeof(uint16_t)));
+        CU(cudaEventCreate(&h->ev0));
+        CU(cudaEventCreate(&h->ev1));
+        CU(cudaMemcpyAsync(h->d_hol, hol.data(), (size_t)E * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));
+        CU(cudaMemsetAsync(h->d_best_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));
+        es_reset_state_kernel<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>(h->d_st, 0, (int)nc);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    });
+    if (rc != CS_OK) {
+        fprintf(stderr, "cs_es_create failed: %s\n", h->err.c_str());
+        es_free(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_es_destroy(cs_es_handle* h) {
+    if (!h) return CS_ERR_INVALID_ARG;
+    es_free(h);
+    delete h;
+    return CS_OK;
+}
+
+extern "C" const char* cs_es_last_error(const cs_es_handle* h) { return h ? h->err.c_str() : ""; }
+
+extern "C" int32_t cs_es_set_stream(cs_es_handle* h, void* s) {
+    return guarded(h, [&] {
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->own_stream) {
+            CU(cudaStreamDestroy(h->stream));
+            h->own_stream = false;
+        }
+        h->stream = (cudaStream_t)s;
+    });
+}
+
+extern "C" int32_t cs_es_init_random(cs_es_handle* h) {
+    return guarded(h, [&] {
+        const int nc = (int)h->cfg.n_chains;
+        es_init_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(h->d_a, h->d_st, h->stride, h->K.E, nc,
+                                                              h->cfg.seed, h->cfg.chain_offset);
+        CU(cudaGetLastError());
+        es_rescore(h, 0, nc);
+        es_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_es_set_chains(cs_es_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
+    return guarded(h, [&] {
+        REQUIRE(rows, "rows is NULL");
+        es_check_range(h, first, count);
+        es_upload(h, first, count, rows);
+        es_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first, (int)count);
+        CU(cudaGetLastError());
+        if (!h->scored && !(first == 0 && count == h->cfg.n_chains))
+            es_rescore(h, 0, (int)h->cfg.n_chains);
+        else
+            es_rescore(h, (int)first, (int)count);
+        es_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_es_get_chains(cs_es_handle* h, uint32_t first, uint32_t count, int64_t* rows) {
+    return guarded(h, [&] {
+        REQUIRE(rows, "rows is NULL");
+        es_check_range(h, first, count);
+        es_download(h, h->d_a, first, count, rows);
+    });
+}
+
+extern "C" int32_t cs_es_get_best_chains(cs_es_handle* h, uint32_t first, uint32_t count, int64_t* rows,
+                                         int64_t* best_hard, int64_t* best_soft) {
+    return guarded(h, [&] {
+        es_check_range(h, first, count);
+        if (rows) es_download(h, h->d_best_a, first, count, rows);
+        if (best_hard || best_soft) {
+            auto st = es_states(h, first, count);
+            for (uint32_t k = 0; k < count; ++k) {
+                if (best_hard) best_hard[k] = st[k].best_hard;
+                if (best_soft) best_soft[k] = st[k].best_soft;
+            }
+        }
+    });
+}
+
+extern "C" int32_t cs_es_get_scores(cs_es_handle* h, int64_t* hard, int64_t* soft) {
+    return guarded(h, [&] {
+        REQUIRE(hard && soft, "hard/soft is NULL");
+        auto st = es_states(h, 0, h->cfg.n_chains);
+        for (size_t k = 0; k < st.size(); ++k) {
+            hard[k] = st[k].hard;
+            soft[k] = st[k].soft;
+        }
+    });
+}
+
+extern "C" int32_t cs_es_get_status(cs_es_handle* h, uint32_t* status) {
+    return guarded(h, [&] {
+        REQUIRE(status, "status is NULL");
+        auto st = es_states(h, 0, h->cfg.n_chains);
+        for (size_t k = 0; k < st.size(); ++k) status[k] = st[k].status;
+    });
+}
+
+extern "C" int32_t cs_es_score_full(cs_es_handle* h, uint32_t chain, int64_t* hard, int64_t* soft,
+                                    int64_t terms[8]) {
+    return guarded(h, [&] {
+        es_check_range(h, chain, 1);
+        long long* d_out = nullptr;
+        CU(cudaMalloc(&d_out, 8 * sizeof(long long)));
+        long long t[8];
+        try {
+            es_full_score_kernel<<<1, 32, 0, h->stream>>>(h->d_a + (size_t)chain * h->stride, h->stride, 1,
+                                                          h->K, h->d_hol, d_out);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(t, d_out, sizeof t, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } catch (...) {
+            cudaFree(d_out);
+            throw;
+        }
+        cudaFree(d_out);
+        if (hard) *hard = t[0] + t[1] + t[2] + t[3];
+        if (soft) *soft = t[4] + t[5] + t[6] + t[7];
+        if (terms)
+            for (int k = 0; k < 8; ++k) terms[k] = t[k];
+    });
+}
+
+extern "C" int32_t cs_es_eval_moves(cs_es_handle* h, uint32_t chain, const cs_es_move* moves,
+                                    uint64_t n_moves, int64_t* dhard, int64_t* dsoft) {
+    return guarded(h, [&] {
+        es_check_range(h, chain, 1);
+        if (n_moves == 0) return;
+        REQUIRE(moves && dhard && dsoft, "moves/dhard/dsoft is NULL");
+        const uint32_t D = h->cfg.n_days, E = h->cfg.n_employees;
+        // split by kind (the kernel takes one kind per launch), keep positions
+        std::vector<uint2> mv[2];
+        std::vector<uint64_t> pos[2];
+        for (uint64_t k = 0; k < n_moves; ++k) {
+            const cs_es_move& m = moves[k];
+            REQUIRE(m.kind <= CS_ES_SWAP, "unknown move kind");
+            REQUIRE(m.a < D && (m.kind == CS_ES_CHANGE ? m.b < E : m.b < D), "move index out of range");
+            mv[m.kind].push_back(make_uint2(m.a, m.b));
+            pos[m.kind].push_back(k);
+        }
+        for (int kind = 0; kind < 2; ++kind) {
+            const size_t cnt = mv[kind].size();
+            if (!cnt) continue;
+            uint2* d_m = nullptr;
+            long long* d_o = nullptr;
+            CU(cudaMalloc(&d_m, cnt * sizeof(uint2)));
+            cudaError_t e = cudaMalloc(&d_o, 2 * cnt * sizeof(long long));
+            if (e != cudaSuccess) {
+                cudaFree(d_m);
+                CU(e);
+            }
+            std::vector<long long> o(2 * cnt);
+            try {
+                CU(cudaMemcpyAsync(d_m, mv[kind].data(), cnt * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+                EsParams p = es_params(h, 0, (int)h->cfg.n_chains);
+                es_eval_kernel<<<1, 256, h->smem, h->stream>>>(p, (int)chain, kind, d_m, cnt, d_o, d_o + cnt);
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(o.data(), d_o, 2 * cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+            } catch (...) {
+                cudaFree(d_m);
+                cudaFree(d_o);
+                throw;
+            }
+            cudaFree(d_m);
+            cudaFree(d_o);
+            for (size_t k = 0; k < cnt; ++k) {
+                dhard[pos[kind][k]] = o[k];
+                dsoft[pos[kind][k]] = o[cnt + k];
+            }
+        }
+    });
+}
+
+extern "C" int32_t cs_es_enumerate(cs_es_handle* h, uint32_t chain, cs_es_move* moves, uint64_t cap,
+                                   uint64_t* n_out) {
+    return guarded(h, [&] {
+        es_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        std::vector<uint16_t> a(h->stride);
+        CU(cudaMemcpyAsync(a.data(), h->d_a + (size_t)chain * h->stride, h->stride * sizeof(uint16_t),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        const uint32_t D = h->cfg.n_days, E = h->cfg.n_employees;
+        uint64_t k = 0;
+        for (uint32_t d = 0; d < D; ++d)
+            for (uint32_t e = 0; e < E; ++e) {
+                if (a[d] == e) continue;
+                if (moves && k < cap) moves[k] = cs_es_move{CS_ES_CHANGE, d, e};
+                ++k;
+            }
+        for (uint32_t d1 = 0; d1 < D; ++d1)
+            for (uint32_t d2 = d1 + 1; d2 < D; ++d2) {
+                if (a[d1] == a[d2]) continue;
+                if (moves && k < cap) moves[k] = cs_es_move{CS_ES_SWAP, d1, d2};
+                ++k;
+            }
+        *n_out = k;
+    });
+}
+
+extern "C" int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, int64_t* dhard,
+                                              int64_t* dsoft, uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        es_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        const uint64_t D = h->cfg.n_days, E = h->cfg.n_employees;
+        const uint64_t cnt = D * E + D * (D - 1) / 2;
+        *n_out = cnt;
+        if (!dhard || !dsoft) return;
+        REQUIRE(cap >= cnt, "delta buffers too small");
+        long long* d_dump = nullptr;
+        CU(cudaMalloc(&d_dump, 2 * cnt * sizeof(long long)));
+        try {
+            EsParams p = es_params(h, (int)chain, 1);
+            p.max_steps = 1;
+            p.dump_h = d_dump;
+            p.dump_s = d_dump + cnt;
+            CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+            es_step_kernel<<<1, h->threads, h->smem, h->stream>>>(p);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(dhard, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(dsoft, d_dump + cnt, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } catch (...) {
+            cudaFree(d_dump);
+            throw;
+        }
+        cudaFree(d_dump);
+    });
+}
+
+extern "C" int32_t cs_es_step(cs_es_handle* h, uint32_t n_steps, cs_es_step_stats* stats) {
+    return guarded(h, [&] { es_run(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0, stats); });
+}
+
+extern "C" int32_t cs_es_local_search(cs_es_handle* h, uint64_t allow, uint64_t max_iterations,
+                                      cs_es_step_stats* stats) {
+    return guarded(h, [&] { es_run(h, 0, (int)h->cfg.n_chains, max_iterations, allow, 1, stats); });
+}
+
+extern "C" int32_t cs_es_local_search_one(cs_es_handle* h, const int64_t* start, uint64_t allow,
+                                          uint64_t max_iterations, int64_t* best, int64_t* best_hard,
+                                          int64_t* best_soft) {
+    return guarded(h, [&] {
+        REQUIRE(start, "start is NULL");
+        es_upload(h, 0, 1, start);
+        es_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, 0, 1);
+        CU(cudaGetLastError());
+        es_rescore(h, 0, h->scored ? 1 : (int)h->cfg.n_chains);
+        h->scored = true;
+        es_run(h, 0, 1, max_iterations, allow, 1, nullptr);
+        if (best) es_download(h, h->d_best_a, 0, 1, best);
+        auto st = es_states(h, 0, 1);
+        if (best_hard) *best_hard = st[0].best_hard;
+        if (best_soft) *best_soft = st[0].best_soft;
+    });
+}
+
+extern "C" int32_t cs_es_get_trace(cs_es_handle* h, uint32_t chain, cs_es_move* moves, int64_t* hard_after,
+                                   int64_t* soft_after, uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        es_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        auto st = es_states(h, chain, 1);
+        *n_out = st[0].steps;
+        uint64_t k = st[0].steps;
+        if (k > h->cfg.trace_capacity) k = h->cfg.trace_capacity;
+        if (k > cap) k = cap;
+        if (k == 0) return;
+        std::vector<EsTraceEntry> t(k);
+        CU(cudaMemcpyAsync(t.data(), h->d_trace + (size_t)chain * h->cfg.trace_capacity,
+                           k * sizeof(EsTraceEntry), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint64_t q = 0; q < k; ++q) {
+            if (moves) moves[q] = cs_es_move{t[q].kind, t[q].x, t[q].y};
+            if (hard_after) hard_after[q] = t[q].hard_after;
+            if (soft_after) soft_after[q] = t[q].soft_after;
+        }
+    });
+}
+
+extern "C" int32_t cs_es_best(cs_es_handle* h, int64_t* rows, int64_t* hard, int64_t* soft, uint32_t* chain) {
+    return guarded(h, [&] {
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        es_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        if (hard) *hard = h->h_stats->best_hard;
+        if (soft) *soft = h->h_stats->best_soft;
+        if (chain) *chain = h->h_stats->best_chain;
+        if (rows) es_download(h, h->d_a, h->h_stats->best_chain, 1, rows);
+    });
+}
+
+extern "C" int32_t cs_es_best_key_device_ptr(cs_es_handle* h, void** dptr) {
+    return guarded(h, [&] {
+        REQUIRE(dptr, "dptr is NULL");
+        *dptr = (void*)&h->d_stats->best_key;
+    });
+}
+
+extern "C" int32_t cs_es_chain_device_ptr(cs_es_handle* h, uint32_t chain, void** dptr, uint32_t* n_slots) {
+    return guarded(h, [&] {
+        es_check_range(h, chain, 1);
+        REQUIRE(dptr, "dptr is NULL");
+        *dptr = (void*)(h->d_a + (size_t)chain * h->stride);
+        if (n_slots) *n_slots = (uint32_t)h->stride;
+    });
+}

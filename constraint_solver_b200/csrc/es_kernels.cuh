@@ -1,0 +1,789 @@
+// Employee-scheduling (on-call rota) chain kernels for sm_100a.
+//
+// Score definition: examples/employee-scheduling/src/lib.rs:261-375 (+ :194-218).  One
+// employee per calendar day; D scored days (<= 64), E employees (dense index 0..E-1).
+//
+// Device formulation.  For every employee e keep the 64-bit day mask m_e (bit d <=> a[d]==e).
+// All four hard terms and S1 are sums over employees of a function of m_e alone:
+//   H1_e = popc(m & holiday_e)                                   (:273-280)
+//   H2_e = popc(m & m>>1)                                        (:286-292)
+//   H3_e = popc(m & m>>7 & SATF) + popc(m & m>>8 & SATF)
+//        + popc(m>>1 & m>>7 & SATF) + popc(m>>1 & m>>8 & SATF)   (:295-315)
+//   H4_e = #{w : popc(m & W14<<w) > 3}                           (:318-327)
+//   S1_e = #{w : popc(m & W7<<w)  > 2}                           (:330-339)
+// so a move's delta on these terms is F(m') - F(m) over the (at most two) employees whose
+// mask changes, with the window loops restricted to windows that overlap a changed day.
+// S2 (weekday affinity, min over employees present on that weekday), S3 (max-min of total
+// days over PRESENT employees) and S4 (max-min of weekend days over present employees) are
+// kept as count histograms + occupancy bitsets, so min/max after a move are bit scans.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace csb {
+
+typedef unsigned long long u64;
+
+constexpr int ES_MAX_DAYS = 64;
+constexpr int ES_CBINS = 12;   // per-weekday count bins 0..11 (a weekday occurs <= 10 times in 64 days)
+constexpr int ES_TBINS = 66;   // total-days bins 0..65
+constexpr int ES_WBINS = 24;   // weekend-day bins 0..23
+constexpr long long ES_KEY_INF = 0x7fffffffffffffffll;
+
+struct EsConst {
+    int D, E, start_wd, n14, n7;
+    u64 valid, wkend, satf;
+    u64 wd[7];
+};
+
+struct EsChainState {
+    long long hard, soft, best_hard, best_soft;
+    unsigned long long moves_scored;
+    unsigned int steps, status;
+};
+
+struct EsTraceEntry {
+    unsigned int kind, x, y, pad;
+    int hard_after, soft_after;
+};
+
+struct EsParams {
+    EsConst K;
+    int first_chain, n_chains, stride;  // stride = D + 1 slots (phantom last, lib.rs:405-412)
+    uint16_t* a;                        // [*, stride] employee index per slot
+    uint16_t* best_a;
+    const u64* hol;  // [E] holiday day-mask per employee
+    EsChainState* st;
+    EsTraceEntry* trace;
+    int trace_cap;
+    unsigned int* work_counter;
+    unsigned long long* totals;
+    unsigned long long max_steps, allow_no_improve;
+    int ls_mode;
+    long long* dump_h;  // debug: every candidate's (dhard, dsoft)
+    long long* dump_s;
+};
+
+// per-chain shared state
+struct EsSmem {
+    u64* mask;          // [E]
+    uint16_t* a;        // [stride]
+    uint16_t* hist2;    // [5][ES_CBINS]
+    uint16_t* histT;    // [ES_TBINS]
+    uint16_t* histW;    // [ES_WBINS]
+    unsigned int* occ2; // [5]  bit c: some employee has exactly c days on that weekday (c>=1)
+    u64* occT;          // [1]  bit c: some employee has exactly c days in total (c>=1)
+    unsigned int* occW; // [1]  bit c: some PRESENT employee has exactly c weekend days (c>=0)
+    int* misc;          // [16] present, distinct[5], hard, soft, ...
+    u64* red;           // [40] reduction scratch
+};
+
+__host__ __device__ inline size_t es_smem_bytes(int D, int E) {
+    size_t b = (size_t)E * 8;                       // mask
+    b += (size_t)((D + 1 + 3) / 4 * 4) * 2;         // a (padded to 8 B)
+    b = (b + 7) / 8 * 8;
+    b += (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2;  // hist
+    b = (b + 7) / 8 * 8;
+    b += 5 * 4 + 4;                                 // occ2 + occW
+    b = (b + 7) / 8 * 8;
+    b += 8;                                         // occT
+    b += 16 * 4;                                    // misc
+    b += 40 * 8;                                    // red
+    return b;
+}
+
+__device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
+    EsSmem s;
+    s.mask = (u64*)p;
+    p += (size_t)E * 8;
+    s.a = (uint16_t*)p;
+    p += (size_t)((D + 1 + 3) / 4 * 4) * 2;
+    p = (unsigned char*)(((uintptr_t)p + 7) / 8 * 8);
+    s.hist2 = (uint16_t*)p;
+    s.histT = s.hist2 + 5 * ES_CBINS;
+    s.histW = s.histT + ES_TBINS;
+    p += (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2;
+    p = (unsigned char*)(((uintptr_t)p + 7) / 8 * 8);
+    s.occ2 = (unsigned int*)p;
+    s.occW = s.occ2 + 5;
+    p += 5 * 4 + 4;
+    p = (unsigned char*)(((uintptr_t)p + 7) / 8 * 8);
+    s.occT = (u64*)p;
+    p += 8;
+    s.misc = (int*)p;
+    p += 16 * 4;
+    s.red = (u64*)p;
+    return s;
+}
+
+enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8 };
+
+// ------------------------------------------------------------------ per-employee terms
+__device__ __forceinline__ int es_pair_terms(u64 m, u64 hol, const EsConst& K) {
+    const u64 m1 = m >> 1, m7 = m >> 7, m8 = m >> 8;
+    return __popcll(m & hol) + __popcll(m & m1) + __popcll(m & m7 & K.satf) +
+           __popcll(m & m8 & K.satf) + __popcll(m1 & m7 & K.satf) + __popcll(m1 & m8 & K.satf);
+}
+
+// windows w in [lo, hi]: #{popc(m & W<<w) > thr}
+__device__ __forceinline__ int es_win_viol(u64 m, u64 W, int lo, int hi, int thr) {
+    int v = 0;
+    for (int w = lo; w <= hi; ++w) v += (__popcll(m & (W << w)) > thr);
+    return v;
+}
+
+// (hard, S1) of employee mask m over all windows
+__device__ __forceinline__ void es_emp_full(u64 m, u64 hol, const EsConst& K, int& hard, int& s1) {
+    hard = es_pair_terms(m, hol, K) + es_win_viol(m, 0x3fffull, 0, K.n14 - 1, 3);
+    s1 = es_win_viol(m, 0x7full, 0, K.n7 - 1, 2);
+}
+
+// delta of (hard, S1) when an employee's mask changes m -> m2
+__device__ __forceinline__ void es_emp_delta(u64 m, u64 m2, u64 hol, const EsConst& K, int& dh,
+                                             int& ds) {
+    dh += es_pair_terms(m2, hol, K) - es_pair_terms(m, hol, K);
+    const u64 x = m ^ m2;
+    const int lo_d = __ffsll((long long)x) - 1, hi_d = 63 - __clzll((long long)x);
+    {   // 14-day windows touching a changed day
+        const int lo = max(0, lo_d - 13), hi = min(K.n14 - 1, hi_d);
+        for (int w = lo; w <= hi; ++w) {
+            const u64 W = 0x3fffull << w;
+            if (!(W & x)) continue;
+            dh += (__popcll(m2 & W) > 3) - (__popcll(m & W) > 3);
+        }
+    }
+    {   // 7-day windows
+        const int lo = max(0, lo_d - 6), hi = min(K.n7 - 1, hi_d);
+        for (int w = lo; w <= hi; ++w) {
+            const u64 W = 0x7full << w;
+            if (!(W & x)) continue;
+            ds += (__popcll(m2 & W) > 2) - (__popcll(m & W) > 2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ histogram helpers
+struct EsAdj {
+    int bin[4], d[4], n;
+    __device__ __forceinline__ EsAdj() : n(0) {}
+    __device__ __forceinline__ void add(int b, int delta) {
+        bin[n] = b;
+        d[n] = delta;
+        ++n;
+    }
+};
+
+// occupancy bitset after applying the adjustments to the histogram
+__device__ __forceinline__ u64 es_occ_after(const uint16_t* hist, u64 occ, const EsAdj& A) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k >= A.n) break;
+        int tot = 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            if (l < A.n && A.bin[l] == A.bin[k]) tot += A.d[l];
+        const int c = (int)hist[A.bin[k]] + tot;
+        const u64 bit = 1ull << A.bin[k];
+        occ = c > 0 ? (occ | bit) : (occ & ~bit);
+    }
+    return occ;
+}
+
+__device__ __forceinline__ int es_spread(u64 occ, int members) {  // max-min, lib.rs:349,363
+    if (members < 2 || occ == 0) return 0;
+    return (63 - __clzll((long long)occ)) - (__ffsll((long long)occ) - 1);
+}
+
+__device__ __forceinline__ int es_s2_term(unsigned int occ, int distinct) {  // lib.rs:206-214
+    return (distinct >= 2 && occ) ? (__ffs((int)occ) - 1) : 0;
+}
+
+// weekday-affinity delta on weekday wd when employee counts change: cm (count c -> c-1) and
+// cp (count c -> c+1); pass -1 to skip one side.
+__device__ __forceinline__ int es_s2_delta(const EsSmem& s, int wd, int cm, int cp) {
+    EsAdj A;
+    int distinct = s.misc[ES_DISTINCT0 + wd];
+    const int old = es_s2_term(s.occ2[wd], distinct);
+    if (cm >= 1) {
+        A.add(cm, -1);
+        if (cm - 1 >= 1) A.add(cm - 1, +1);
+        else --distinct;
+    }
+    if (cp >= 0) {
+        if (cp >= 1) A.add(cp, -1);
+        else ++distinct;
+        A.add(cp + 1, +1);
+    }
+    const unsigned int occ = (unsigned int)es_occ_after(s.hist2 + wd * ES_CBINS, s.occ2[wd], A);
+    return es_s2_term(occ, distinct) - old;
+}
+
+__device__ __forceinline__ int es_weekday(const EsConst& K, int d) { return (K.start_wd + d) % 7; }
+
+// ------------------------------------------------------------------ move deltas
+// change: day d gets employee en (!= current).  Returns (dhard, dsoft).
+__device__ __forceinline__ void es_change_delta(const EsSmem& s, const EsConst& K,
+                                                const u64* __restrict__ hol, int d, int en,
+                                                int& dh, int& ds) {
+    const int eo = s.a[d];
+    const u64 bit = 1ull << d;
+    const u64 mo = s.mask[eo], mn = s.mask[en];
+    dh = 0;
+    ds = 0;
+    es_emp_delta(mo, mo & ~bit, hol[eo], K, dh, ds);
+    es_emp_delta(mn, mn | bit, hol[en], K, dh, ds);
+    const int wd = es_weekday(K, d);
+    if (wd < 5) ds += es_s2_delta(s, wd, __popcll(mo & K.wd[wd]), __popcll(mn & K.wd[wd]));
+    // S3 / S4 over present employees
+    const int to = __popcll(mo), tn = __popcll(mn);
+    const int wo = __popcll(mo & K.wkend), wn = __popcll(mn & K.wkend);
+    const int isw = (K.wkend & bit) ? 1 : 0;
+    int present = s.misc[ES_PRESENT];
+    const int oldT = es_spread(*s.occT, present), oldW = es_spread((u64)*s.occW, present);
+    EsAdj T, W;
+    T.add(to, -1);
+    W.add(wo, -1);
+    if (to - 1 >= 1) {
+        T.add(to - 1, +1);
+        W.add(wo - isw, +1);
+    } else {
+        --present;
+    }
+    if (tn >= 1) {
+        T.add(tn, -1);
+        W.add(wn, -1);
+    } else {
+        ++present;
+    }
+    T.add(tn + 1, +1);
+    W.add(wn + isw, +1);
+    const u64 occT = es_occ_after(s.histT, *s.occT, T);
+    const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
+    ds += es_spread(occT, present) - oldT + es_spread(occW, present) - oldW;
+}
+
+// swap: days d1 < d2 exchange employees (different).
+__device__ __forceinline__ void es_swap_delta(const EsSmem& s, const EsConst& K,
+                                              const u64* __restrict__ hol, int d1, int d2, int& dh,
+                                              int& ds) {
+    const int e1 = s.a[d1], e2 = s.a[d2];
+    const u64 b1 = 1ull << d1, b2 = 1ull << d2, x = b1 | b2;
+    const u64 m1 = s.mask[e1], m2 = s.mask[e2];
+    dh = 0;
+    ds = 0;
+    es_emp_delta(m1, m1 ^ x, hol[e1], K, dh, ds);
+    es_emp_delta(m2, m2 ^ x, hol[e2], K, dh, ds);
+    const int wd1 = es_weekday(K, d1), wd2 = es_weekday(K, d2);
+    if (wd1 != wd2) {
+        // the two weekdays are distinct histograms, so their deltas are independent
+        if (wd1 < 5)
+            ds += es_s2_delta(s, wd1, __popcll(m1 & K.wd[wd1]), __popcll(m2 & K.wd[wd1]));
+        if (wd2 < 5)
+            ds += es_s2_delta(s, wd2, __popcll(m2 & K.wd[wd2]), __popcll(m1 & K.wd[wd2]));
+    }
+    const int k1 = (K.wkend & b1) ? 1 : 0, k2 = (K.wkend & b2) ? 1 : 0;
+    if (k1 != k2) {  // totals (S3) unchanged; weekend counts move between the two employees
+        const int present = s.misc[ES_PRESENT];
+        const int w1 = __popcll(m1 & K.wkend), w2 = __popcll(m2 & K.wkend);
+        EsAdj W;
+        W.add(w1, -1);
+        W.add(w1 - k1 + k2, +1);
+        W.add(w2, -1);
+        W.add(w2 + k1 - k2, +1);
+        const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
+        ds += es_spread(occW, present) - es_spread((u64)*s.occW, present);
+    }
+}
+
+// ------------------------------------------------------------------ tallies (K4)
+// Build masks + histograms from a[] and the full score from them.  Block-cooperative.
+__device__ void es_build(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol,
+                         int& hard, int& soft) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < K.E; e += nt) s.mask[e] = 0;
+    for (int k = tid; k < 5 * ES_CBINS + ES_TBINS + ES_WBINS; k += nt) s.hist2[k] = 0;
+    if (tid < 5) s.occ2[tid] = 0;
+    if (tid < 16) s.misc[tid] = 0;
+    if (tid == 0) {
+        *s.occT = 0;
+        *s.occW = 0;
+    }
+    __syncthreads();
+    for (int d = tid; d < K.D; d += nt) atomicOr(&s.mask[s.a[d]], 1ull << d);
+    __syncthreads();
+    int h = 0, s1 = 0;
+    for (int e = tid; e < K.E; e += nt) {
+        const u64 m = s.mask[e];
+        if (!m) continue;
+        int eh, es;
+        es_emp_full(m, hol[e], K, eh, es);
+        h += eh;
+        s1 += es;
+        atomicAdd(&s.misc[ES_PRESENT], 1);
+        const int t = __popcll(m), w = __popcll(m & K.wkend);
+        // 16-bit histogram bins: add through the containing 32-bit word
+        {
+            const int idx = (int)(s.histT - s.hist2) + t;
+            atomicAdd((unsigned int*)s.hist2 + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
+            const int idw = (int)(s.histW - s.hist2) + w;
+            atomicAdd((unsigned int*)s.hist2 + (idw >> 1), (idw & 1) ? 0x10000u : 1u);
+        }
+        atomicOr(s.occT, 1ull << t);
+        atomicOr(s.occW, 1u << w);
+        for (int wd = 0; wd < 5; ++wd) {
+            const int c = __popcll(m & K.wd[wd]);
+            if (!c) continue;
+            const int idx = wd * ES_CBINS + c;
+            atomicAdd((unsigned int*)s.hist2 + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
+            atomicOr(&s.occ2[wd], 1u << c);
+            atomicAdd(&s.misc[ES_DISTINCT0 + wd], 1);
+        }
+    }
+    atomicAdd(&s.misc[ES_HARD], h);
+    atomicAdd(&s.misc[ES_SOFT], s1);
+    __syncthreads();
+    hard = s.misc[ES_HARD];
+    soft = s.misc[ES_SOFT];
+    const int present = s.misc[ES_PRESENT];
+    for (int wd = 0; wd < 5; ++wd) soft += es_s2_term(s.occ2[wd], s.misc[ES_DISTINCT0 + wd]);
+    soft += es_spread(*s.occT, present) + es_spread((u64)*s.occW, present);
+    __syncthreads();
+}
+
+// single-thread application of an accepted move to the tallies
+__device__ void es_hist_move(uint16_t* hist, unsigned int* occ32, u64* occ64, int from, int to) {
+    // from/to < 0 : no such side
+    if (from >= 0) {
+        if (--hist[from] == 0) {
+            if (occ64) *occ64 &= ~(1ull << from);
+            else *occ32 &= ~(1u << from);
+        }
+    }
+    if (to >= 0) {
+        if (hist[to]++ == 0) {
+            if (occ64) *occ64 |= 1ull << to;
+            else *occ32 |= 1u << to;
+        }
+    }
+}
+
+__device__ void es_set_mask(const EsSmem& s, const EsConst& K, int e, u64 m2) {
+    const u64 m = s.mask[e];
+    const int t = __popcll(m), t2 = __popcll(m2);
+    const int w = __popcll(m & K.wkend), w2 = __popcll(m2 & K.wkend);
+    if (t != t2 || w != w2) {
+        es_hist_move(s.histT, nullptr, s.occT, t >= 1 ? t : -1, t2 >= 1 ? t2 : -1);
+        es_hist_move(s.histW, s.occW, nullptr, t >= 1 ? w : -1, t2 >= 1 ? w2 : -1);
+        s.misc[ES_PRESENT] += (t2 >= 1) - (t >= 1);
+    }
+    for (int wd = 0; wd < 5; ++wd) {
+        const int c = __popcll(m & K.wd[wd]), c2 = __popcll(m2 & K.wd[wd]);
+        if (c == c2) continue;
+        es_hist_move(s.hist2 + wd * ES_CBINS, &s.occ2[wd], nullptr, c >= 1 ? c : -1,
+                     c2 >= 1 ? c2 : -1);
+        s.misc[ES_DISTINCT0 + wd] += (c2 >= 1) - (c >= 1);
+    }
+    s.mask[e] = m2;
+}
+
+// move id: change (d, e) -> d*E + e ; swap (d1<d2) -> D*E + tri(d1,d2)
+__device__ __forceinline__ int es_tri_index(int D, int d1, int d2) {
+    return d1 * D - d1 * (d1 + 1) / 2 + (d2 - d1 - 1);
+}
+
+__device__ __forceinline__ long long es_key(int dh, int ds, int id) {
+    return ((long long)(dh + 32768) << 44) | ((long long)(ds + 32768) << 24) | (long long)id;
+}
+
+__device__ __forceinline__ long long es_block_min(long long key, u64* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other < key ? other : key;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = (u64)key;
+    __syncthreads();
+    if (w == 0) {
+        long long x = (l < nw) ? (long long)red[l] : ES_KEY_INF;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long other = __shfl_xor_sync(0xffffffffu, x, o);
+            x = other < x ? other : x;
+        }
+        if (l == 0) red[32] = (u64)x;
+    }
+    __syncthreads();
+    const long long out = (long long)red[32];
+    __syncthreads();
+    return out;
+}
+
+// ------------------------------------------------------------------ the step kernel (K5)
+__global__ void es_step_kernel(EsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const EsConst& K = p.K;
+    const EsSmem s = es_carve(smem_raw, K.D, K.E);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int D = K.D, E = K.E;
+    const int n_change = D * E, n_swap = D * (D - 1) / 2, n_moves = n_change + n_swap;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s.misc[ES_BCAST] = (int)atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const int local = s.misc[ES_BCAST];
+        if (local >= p.n_chains) break;
+        const int chain = p.first_chain + local;
+        uint16_t* ga = p.a + (size_t)chain * p.stride;
+        EsChainState* st = p.st + chain;
+        __syncthreads();
+        for (int k = tid; k < p.stride; k += nt) s.a[k] = ga[k];
+        __syncthreads();
+        int hard, soft;
+        es_build(s, K, p.hol, hard, soft);
+        int best_h = p.ls_mode ? hard : (int)st->best_hard;
+        int best_s = p.ls_mode ? soft : (int)st->best_soft;
+        if (p.ls_mode)
+            for (int k = tid; k < p.stride; k += nt) p.best_a[(size_t)chain * p.stride + k] = s.a[k];
+        unsigned long long no_improve = 0, scored = 0;
+        const unsigned int steps0 = st->steps;
+        unsigned int steps = steps0, status = 0;
+
+        for (unsigned long long it = 0; it < p.max_steps; ++it) {
+            if (hard == 0 && soft == 0) {  // is_best, lib.rs:245-249
+                status = 1;
+                best_h = 0;
+                best_s = 0;
+                break;
+            }
+            long long key = ES_KEY_INF;
+            unsigned int nscored = 0;
+            for (int id = tid; id < n_moves; id += nt) {
+                int dh, ds;
+                bool ok;
+                if (id < n_change) {
+                    const int d = id / E, e = id - d * E;
+                    ok = (s.a[d] != e);
+                    if (ok) es_change_delta(s, K, p.hol, d, e, dh, ds);
+                } else {
+                    // decode the triangular index (d1 < d2)
+                    int r = id - n_change, d1 = 0;
+                    while (r >= D - 1 - d1) {
+                        r -= D - 1 - d1;
+                        ++d1;
+                    }
+                    const int d2 = d1 + 1 + r;
+                    ok = (s.a[d1] != s.a[d2]);
+                    if (ok) es_swap_delta(s, K, p.hol, d1, d2, dh, ds);
+                }
+                if (p.dump_h) {
+                    p.dump_h[id] = ok ? (long long)dh : INT64_MAX;
+                    p.dump_s[id] = ok ? (long long)ds : INT64_MAX;
+                }
+                if (ok) {
+                    ++nscored;
+                    const long long k2 = es_key(dh, ds, id);
+                    key = k2 < key ? k2 : key;
+                }
+            }
+            key = es_block_min(key, s.red);
+            {   // count the candidates scored (block sum through the same scratch)
+                unsigned int c = nscored;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if ((tid & 31) == 0) atomicAdd((unsigned int*)&s.misc[ES_BCAST + 1], c);
+                __syncthreads();
+                scored += (unsigned int)s.misc[ES_BCAST + 1];
+                __syncthreads();
+                if (tid == 0) s.misc[ES_BCAST + 1] = 0;
+            }
+            if (p.dump_h) break;
+            if (key == ES_KEY_INF) {  // empty neighbourhood, local_search.rs:336-338
+                status = 3;
+                break;
+            }
+            const int dh = (int)((key >> 44) & 0xffff) - 32768;
+            const int ds = (int)((key >> 24) & 0xfffff) - 32768;
+            const int id = (int)(key & 0xffffff);
+            const bool improved = dh < 0 || (dh == 0 && ds < 0);  // lexicographic (hard, soft)
+            if (!improved) {
+                ++no_improve;
+                if (p.allow_no_improve && no_improve >= p.allow_no_improve) {
+                    status = 2;
+                    break;
+                }
+            } else {
+                no_improve = 0;
+            }
+            hard += dh;
+            soft += ds;
+            if (tid == 0) {
+                unsigned int kind, x, y;
+                if (id < n_change) {
+                    const int d = id / E, e = id - d * E, eo = s.a[d];
+                    const u64 bit = 1ull << d;
+                    es_set_mask(s, K, eo, s.mask[eo] & ~bit);
+                    es_set_mask(s, K, e, s.mask[e] | bit);
+                    s.a[d] = (uint16_t)e;
+                    kind = 0;
+                    x = (unsigned)d;
+                    y = (unsigned)e;
+                } else {
+                    int r = id - n_change, d1 = 0;
+                    while (r >= D - 1 - d1) {
+                        r -= D - 1 - d1;
+                        ++d1;
+                    }
+                    const int d2 = d1 + 1 + r, e1 = s.a[d1], e2 = s.a[d2];
+                    const u64 x2 = (1ull << d1) | (1ull << d2);
+                    es_set_mask(s, K, e1, s.mask[e1] ^ x2);
+                    es_set_mask(s, K, e2, s.mask[e2] ^ x2);
+                    s.a[d1] = (uint16_t)e2;
+                    s.a[d2] = (uint16_t)e1;
+                    kind = 1;
+                    x = (unsigned)d1;
+                    y = (unsigned)d2;
+                }
+                if (p.trace && steps < (unsigned)p.trace_cap) {
+                    EsTraceEntry t;
+                    t.kind = kind;
+                    t.x = x;
+                    t.y = y;
+                    t.pad = 0;
+                    t.hard_after = hard;
+                    t.soft_after = soft;
+                    p.trace[(size_t)chain * p.trace_cap + steps] = t;
+                }
+            }
+            ++steps;
+            __syncthreads();
+            if (improved) {
+                best_h = hard;
+                best_s = soft;
+                for (int k = tid; k < p.stride; k += nt)
+                    p.best_a[(size_t)chain * p.stride + k] = s.a[k];
+            }
+        }
+        __syncthreads();
+        if (p.dump_h) continue;
+        for (int k = tid; k < p.stride; k += nt) ga[k] = s.a[k];
+        if (tid == 0) {
+            st->hard = hard;
+            st->soft = soft;
+            st->best_hard = best_h;
+            st->best_soft = best_s;
+            st->moves_scored += scored;
+            st->steps = steps;
+            st->status = status;
+            atomicAdd(p.totals, scored);
+            atomicAdd(p.totals + 1, (unsigned long long)(steps - steps0));
+        }
+    }
+}
+
+// (re)score chains from the tallies after set/init: fills hard/soft/best and best_a
+__global__ void es_rescore_kernel(EsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const EsSmem s = es_carve(smem_raw, p.K.D, p.K.E);
+    for (int local = blockIdx.x; local < p.n_chains; local += gridDim.x) {
+        const int chain = p.first_chain + local;
+        __syncthreads();
+        for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
+            s.a[k] = p.a[(size_t)chain * p.stride + k];
+        __syncthreads();
+        int hard, soft;
+        es_build(s, p.K, p.hol, hard, soft);
+        for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
+            p.best_a[(size_t)chain * p.stride + k] = s.a[k];
+        if (threadIdx.x == 0) {
+            EsChainState z = p.st[chain];
+            z.hard = hard;
+            z.soft = soft;
+            z.best_hard = hard;
+            z.best_soft = soft;
+            z.status = (hard == 0 && soft == 0) ? 1u : 0u;
+            p.st[chain] = z;
+        }
+    }
+}
+
+// explicit-move deltas against one chain (parity hook); kind 0 change (x=day,y=employee idx),
+// 1 swap (x,y = days)
+__global__ void es_eval_kernel(EsParams p, int chain, int kind, const uint2* __restrict__ moves,
+                               unsigned long long n_moves, long long* __restrict__ dh_out,
+                               long long* __restrict__ ds_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const EsSmem s = es_carve(smem_raw, p.K.D, p.K.E);
+    for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
+        s.a[k] = p.a[(size_t)chain * p.stride + k];
+    __syncthreads();
+    int hard, soft;
+    es_build(s, p.K, p.hol, hard, soft);
+    for (unsigned long long k = threadIdx.x; k < n_moves; k += blockDim.x) {
+        const uint2 mv = moves[k];
+        int dh = 0, ds = 0;
+        bool ok;
+        if (kind == 0) {
+            ok = s.a[mv.x] != mv.y;
+            if (ok) es_change_delta(s, p.K, p.hol, (int)mv.x, (int)mv.y, dh, ds);
+        } else {
+            const int d1 = (int)min(mv.x, mv.y), d2 = (int)max(mv.x, mv.y);
+            ok = d1 != d2 && s.a[d1] != s.a[d2];
+            if (ok) es_swap_delta(s, p.K, p.hol, d1, d2, dh, ds);
+        }
+        dh_out[k] = ok ? (long long)dh : INT64_MAX;
+        ds_out[k] = ok ? (long long)ds : INT64_MAX;
+    }
+}
+
+// K6: full re-score straight from a[] by the reference's own loops (no masks, no
+// histograms) -- one thread per chain; cross-checks the tally formulation.
+__global__ void es_full_score_kernel(const uint16_t* __restrict__ a, int stride, int n_chains,
+                                     EsConst K, const u64* __restrict__ hol, long long* out8) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    const uint16_t* x = a + (size_t)chain * stride;
+    const int D = K.D;
+    long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int d = 0; d < D; ++d) t[0] += (hol[x[d]] >> d) & 1ull;           // lib.rs:273-280
+    for (int i = 0; i + 2 <= D; ++i) t[1] += (x[i] == x[i + 1]);           // :286-292
+    for (int i = 0; i + 9 <= D; ++i) {                                     // :295-315
+        if ((K.start_wd + i) % 7 != 5) continue;
+        t[2] += (x[i] == x[i + 7]) + (x[i] == x[i + 8]) + (x[i + 1] == x[i + 7]) +
+                (x[i + 1] == x[i + 8]);
+    }
+    for (int len = 14; len >= 7; len -= 7) {                               // :318-339
+        const int limit = len == 14 ? 3 : 2;
+        for (int w = 0; w + len <= D; ++w)
+            for (int q = w; q < w + len; ++q) {
+                bool first = true;
+                for (int r = w; r < q; ++r)
+                    if (x[r] == x[q]) first = false;
+                if (!first) continue;
+                int c = 0;
+                for (int r = q; r < w + len; ++r) c += (x[r] == x[q]);
+                if (c > limit) t[len == 14 ? 3 : 4] += 1;
+            }
+    }
+    for (int wd = 0; wd < 5; ++wd) {                                       // :194-218
+        int distinct = 0, minc = 1 << 30;
+        for (int i = 0; i < D; ++i) {
+            if ((K.start_wd + i) % 7 != wd) continue;
+            bool first = true;
+            for (int q = 0; q < i; ++q)
+                if ((K.start_wd + q) % 7 == wd && x[q] == x[i]) first = false;
+            if (!first) continue;
+            int c = 0;
+            for (int q = i; q < D; ++q) c += ((K.start_wd + q) % 7 == wd && x[q] == x[i]);
+            ++distinct;
+            minc = c < minc ? c : minc;
+        }
+        if (distinct >= 2) t[5] += minc;
+    }
+    int present = 0, mind = 1 << 30, maxd = -1, minw = 1 << 30, maxw = -1;  // :345-365
+    for (int i = 0; i < D; ++i) {
+        bool first = true;
+        for (int q = 0; q < i; ++q)
+            if (x[q] == x[i]) first = false;
+        if (!first) continue;
+        int days = 0, wk = 0;
+        for (int q = i; q < D; ++q)
+            if (x[q] == x[i]) {
+                ++days;
+                const int w = (K.start_wd + q) % 7;
+                wk += (w == 5 || w == 6);
+            }
+        ++present;
+        mind = days < mind ? days : mind;
+        maxd = days > maxd ? days : maxd;
+        minw = wk < minw ? wk : minw;
+        maxw = wk > maxw ? wk : maxw;
+    }
+    if (present >= 2) {
+        t[6] = maxd - mind;
+        t[7] = maxw - minw;
+    }
+    for (int k = 0; k < 8; ++k) out8[(size_t)chain * 8 + k] = t[k];
+}
+
+// initial solution: uniform random employee per slot, phantom slot included
+// (examples/employee-scheduling/src/lib.rs:404-419); draw s of stream (seed, chain, INIT).
+__global__ void es_init_kernel(uint16_t* a, EsChainState* st, int stride, int E, int n_chains,
+                               unsigned long long seed, unsigned int chain_offset) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    PhiloxDraws d(seed, chain_offset + (unsigned)chain, 0u);
+    for (int k = 0; k < stride; ++k) a[(size_t)chain * stride + k] = (uint16_t)d.below((unsigned)E);
+    EsChainState z;
+    z.hard = z.soft = z.best_hard = z.best_soft = -1;
+    z.moves_scored = 0;
+    z.steps = 0;
+    z.status = 0;
+    st[chain] = z;
+}
+
+__global__ void es_reset_state_kernel(EsChainState* st, int first, int count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    EsChainState z;
+    z.hard = z.soft = z.best_hard = z.best_soft = -1;
+    z.moves_scored = 0;
+    z.steps = 0;
+    z.status = 0;
+    st[first + k] = z;
+}
+
+struct EsStats {
+    long long best_hard, best_soft, best_key;
+    unsigned int best_chain, chains_at_best, chains_feasible, pad;
+};
+
+// best chain by lexicographic (hard, soft); key = (hard<<44 | soft<<24... ) packs into
+// (hard << 48) | (soft << 32) | global chain id for the min-allreduce
+__global__ void es_stats_kernel(const EsChainState* __restrict__ st, int n_chains,
+                                unsigned int chain_offset, EsStats* out) {
+    __shared__ long long skey[32];
+    __shared__ unsigned int sa[32], sf[32];
+    long long key = ES_KEY_INF;
+    unsigned int ab = 0, fe = 0;
+    for (int c = threadIdx.x; c < n_chains; c += blockDim.x) {
+        const EsChainState x = st[c];
+        const long long k = (x.hard << 48) | (x.soft << 32) | (long long)(unsigned)c;
+        key = k < key ? k : key;
+        ab += (x.hard == 0 && x.soft == 0);
+        fe += (x.hard == 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+        key = ok < key ? ok : key;
+        ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        fe += __shfl_xor_sync(0xffffffffu, fe, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        skey[w] = key;
+        sa[w] = ab;
+        sf[w] = fe;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            key = skey[k] < key ? skey[k] : key;
+            ab += sa[k];
+            fe += sf[k];
+        }
+        out->best_hard = key >> 48;
+        out->best_soft = (key >> 32) & 0xffff;
+        out->best_chain = (unsigned)(key & 0xffffffffll);
+        out->best_key = (key & ~0xffffffffll) | (long long)(out->best_chain + chain_offset);
+        out->chains_at_best = ab;
+        out->chains_feasible = fe;
+    }
+}
+
+}  // namespace csb

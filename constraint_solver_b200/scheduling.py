@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's employee-scheduling plug-in over the C ABI.
+
+Mirrors examples/employee-scheduling/src/lib.rs: Employee (:119-122), ScheduleSolution
+(:127-146, `date_to_employee` with its phantom slot), ScheduleScore (:239-249),
+ScheduleSolutionScoreCalculator (:251-375), ScheduleInitialSolutionGenerator (:377-420),
+the change/swap move types (:422-491) and get_ils-style construction (:57-117).  Everything
+is computed on the device through libcs_b200.so; dates are reduced to (start weekday, D).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime as _dt
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+CHANGE, SWAP = L.CS_ES_CHANGE, L.CS_ES_SWAP
+INT64_MAX = np.iinfo(np.int64).max
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+@dataclass(frozen=True, order=True)
+class ScheduleScore:
+    """lib.rs:239-249: ordered lexicographically hard then soft."""
+    hard_score: float
+    soft_score: float
+
+    def is_best(self) -> bool:
+        return self.hard_score == 0.0 and self.soft_score == 0.0
+
+
+@dataclass
+class EsStepStats:
+    moves_scored: int
+    steps_accepted: int
+    best_hard: int
+    best_soft: int
+    best_chain: int
+    chains_at_best: int
+    chains_feasible: int
+    device_ms: float
+    kernel_launches: int
+
+
+def weekday_of(date: _dt.date) -> int:
+    return date.weekday()  # Monday = 0, like chrono's num_days_from_monday
+
+
+class ScheduleChains:
+    """Batch engine: n_chains independent rota chains on one GPU.
+
+    employees: iterable of int ids.  holidays: iterable of (employee_id, day_index).
+    A solution row has n_days + 1 entries (phantom last slot, lib.rs:405-412).
+    """
+
+    def __init__(self, n_days: int, employees: Sequence[int], *, start_weekday: int = 0,
+                 holidays=(), n_chains: int = 1, seed: int = 42, chain_offset: int = 0,
+                 trace_capacity: int = 0, device: int = -1):
+        self._lib = L.load()
+        self.n_days = int(n_days)
+        self.n_slots = self.n_days + 1
+        self.employees = np.ascontiguousarray(sorted(int(e) for e in employees), dtype=np.int64)
+        self.n_employees = len(self.employees)
+        self.n_chains = int(n_chains)
+        self.trace_capacity = trace_capacity
+        self.chain_offset = chain_offset
+        hol = np.asarray(list(holidays), dtype=np.int64).reshape(-1, 2)
+        he = np.ascontiguousarray(hol[:, 0]) if len(hol) else np.zeros(1, np.int64)
+        hd = np.ascontiguousarray(hol[:, 1]) if len(hol) else np.zeros(1, np.int64)
+        cfg = L.CsEsConfig(n_days=n_days, n_employees=self.n_employees, start_weekday=start_weekday,
+                           n_chains=n_chains, chain_offset=chain_offset,
+                           trace_capacity=trace_capacity, seed=seed, device=device, reserved=0)
+        ids = np.ascontiguousarray(np.asarray(list(employees), dtype=np.int64))
+        h = C.c_void_p()
+        rc = self._lib.cs_es_create(C.byref(cfg), _ptr(ids), _ptr(he), _ptr(hd), len(hol), C.byref(h))
+        if rc != L.CS_OK:
+            raise L.CsError(rc, "cs_es_create", L.status_string(rc))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cs_es_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, where):
+        if rc != L.CS_OK:
+            raise L.CsError(rc, where, self._lib.cs_es_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.cs_es_set_stream(self._h, C.c_void_p(cuda_stream)), "cs_es_set_stream")
+
+    def init_random(self):
+        self._check(self._lib.cs_es_init_random(self._h), "cs_es_init_random")
+
+    def _rows(self, rows):
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int64))
+        if rows.ndim == 1:
+            rows = rows[None, :]
+        if rows.shape[1] == self.n_days:  # no phantom supplied: repeat the last day
+            rows = np.ascontiguousarray(np.concatenate([rows, rows[:, -1:]], axis=1))
+        if rows.shape[1] != self.n_slots:
+            raise ValueError("rows must have n_days + 1 (or n_days) entries")
+        return rows
+
+    def set_chains(self, rows, first_chain: int = 0):
+        rows = self._rows(rows)
+        self._check(self._lib.cs_es_set_chains(self._h, first_chain, rows.shape[0], _ptr(rows)),
+                    "cs_es_set_chains")
+
+    def set_chains_ptr(self, host_ptr: int, count: int, first_chain: int = 0):
+        self._check(self._lib.cs_es_set_chains(self._h, first_chain, count, C.c_void_p(host_ptr)),
+                    "cs_es_set_chains")
+
+    def get_chains(self, first_chain: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n_chains - first_chain if count is None else count
+        out = np.empty((count, self.n_slots), dtype=np.int64)
+        self._check(self._lib.cs_es_get_chains(self._h, first_chain, count, _ptr(out)), "cs_es_get_chains")
+        return out
+
+    def get_best_chains(self, first_chain: int = 0, count: Optional[int] = None):
+        count = self.n_chains - first_chain if count is None else count
+        out = np.empty((count, self.n_slots), dtype=np.int64)
+        bh = np.empty(count, dtype=np.int64)
+        bs = np.empty(count, dtype=np.int64)
+        self._check(self._lib.cs_es_get_best_chains(self._h, first_chain, count, _ptr(out), _ptr(bh), _ptr(bs)),
+                    "cs_es_get_best_chains")
+        return out, bh, bs
+
+    def scores(self):
+        hard = np.empty(self.n_chains, dtype=np.int64)
+        soft = np.empty(self.n_chains, dtype=np.int64)
+        self._check(self._lib.cs_es_get_scores(self._h, _ptr(hard), _ptr(soft)), "cs_es_get_scores")
+        return hard, soft
+
+    def status(self):
+        out = np.empty(self.n_chains, dtype=np.uint32)
+        self._check(self._lib.cs_es_get_status(self._h, _ptr(out)), "cs_es_get_status")
+        return out
+
+    def score_full(self, chain: int = 0):
+        hard, soft = C.c_int64(), C.c_int64()
+        terms = (C.c_int64 * 8)()
+        self._check(self._lib.cs_es_score_full(self._h, chain, C.byref(hard), C.byref(soft), terms),
+                    "cs_es_score_full")
+        return int(hard.value), int(soft.value), [int(x) for x in terms]
+
+    @staticmethod
+    def _moves(kind, a, b):
+        kind = np.broadcast_to(np.asarray(kind, dtype=np.uint32), np.shape(a))
+        mv = np.zeros(len(a), dtype=[("kind", np.uint32), ("a", np.uint32), ("b", np.uint32)])
+        mv["kind"], mv["a"], mv["b"] = kind, a, b
+        return mv
+
+    def eval_moves(self, kind, a, b, chain: int = 0):
+        mv = self._moves(kind, np.asarray(a), np.asarray(b))
+        dh = np.empty(max(len(mv), 1), dtype=np.int64)
+        ds = np.empty(max(len(mv), 1), dtype=np.int64)
+        self._check(self._lib.cs_es_eval_moves(self._h, chain, _ptr(mv), len(mv), _ptr(dh), _ptr(ds)),
+                    "cs_es_eval_moves")
+        return dh[: len(mv)], ds[: len(mv)]
+
+    def enumerate(self, chain: int = 0):
+        n = C.c_uint64()
+        self._check(self._lib.cs_es_enumerate(self._h, chain, None, 0, C.byref(n)), "cs_es_enumerate")
+        mv = np.zeros(max(n.value, 1), dtype=[("kind", np.uint32), ("a", np.uint32), ("b", np.uint32)])
+        self._check(self._lib.cs_es_enumerate(self._h, chain, _ptr(mv), n.value, C.byref(n)), "cs_es_enumerate")
+        return mv[: n.value]
+
+    def neighbourhood_deltas(self, chain: int = 0):
+        n = C.c_uint64()
+        self._check(self._lib.cs_es_neighbourhood_deltas(self._h, chain, None, None, 0, C.byref(n)),
+                    "cs_es_neighbourhood_deltas")
+        dh = np.empty(max(n.value, 1), dtype=np.int64)
+        ds = np.empty(max(n.value, 1), dtype=np.int64)
+        self._check(self._lib.cs_es_neighbourhood_deltas(self._h, chain, _ptr(dh), _ptr(ds), n.value, C.byref(n)),
+                    "cs_es_neighbourhood_deltas")
+        return dh[: n.value], ds[: n.value]
+
+    @staticmethod
+    def _stats(s):
+        return EsStepStats(int(s.moves_scored), int(s.steps_accepted), int(s.best_hard), int(s.best_soft),
+                           int(s.best_chain), int(s.chains_at_best), int(s.chains_feasible),
+                           float(s.device_ms), int(s.kernel_launches))
+
+    def step(self, n_steps: int = 1) -> EsStepStats:
+        s = L.CsEsStepStats()
+        self._check(self._lib.cs_es_step(self._h, n_steps, C.byref(s)), "cs_es_step")
+        return self._stats(s)
+
+    def local_search(self, allow_no_improvement_for: int, max_iterations: int) -> EsStepStats:
+        s = L.CsEsStepStats()
+        self._check(self._lib.cs_es_local_search(self._h, allow_no_improvement_for, max_iterations, C.byref(s)),
+                    "cs_es_local_search")
+        return self._stats(s)
+
+    def local_search_one(self, start, allow_no_improvement_for: int, max_iterations: int):
+        start = self._rows(start)[0]
+        best = np.empty(self.n_slots, dtype=np.int64)
+        bh, bs = C.c_int64(), C.c_int64()
+        self._check(self._lib.cs_es_local_search_one(self._h, _ptr(start), allow_no_improvement_for,
+                                                     max_iterations, _ptr(best), C.byref(bh), C.byref(bs)),
+                    "cs_es_local_search_one")
+        return best, int(bh.value), int(bs.value)
+
+    def trace(self, chain: int = 0):
+        n = C.c_uint64()
+        cap = max(self.trace_capacity, 1)
+        mv = np.zeros(cap, dtype=[("kind", np.uint32), ("a", np.uint32), ("b", np.uint32)])
+        hard = np.empty(cap, dtype=np.int64)
+        soft = np.empty(cap, dtype=np.int64)
+        self._check(self._lib.cs_es_get_trace(self._h, chain, _ptr(mv), _ptr(hard), _ptr(soft), cap, C.byref(n)),
+                    "cs_es_get_trace")
+        k = min(int(n.value), self.trace_capacity)
+        return mv[:k], hard[:k], soft[:k], int(n.value)
+
+    def best(self):
+        rows = np.empty(self.n_slots, dtype=np.int64)
+        h, s, c = C.c_int64(), C.c_int64(), C.c_uint32()
+        self._check(self._lib.cs_es_best(self._h, _ptr(rows), C.byref(h), C.byref(s), C.byref(c)), "cs_es_best")
+        return rows, int(h.value), int(s.value), int(c.value)
+
+    def best_key_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.cs_es_best_key_device_ptr(self._h, C.byref(p)), "cs_es_best_key_device_ptr")
+        return int(p.value)
+
+    def chain_device_ptr(self, chain: int):
+        p, n = C.c_void_p(), C.c_uint32()
+        self._check(self._lib.cs_es_chain_device_ptr(self._h, chain, C.byref(p), C.byref(n)),
+                    "cs_es_chain_device_ptr")
+        return int(p.value), int(n.value)
+
+
+class ScheduleSolutionScoreCalculator:
+    """lib.rs:251-375 shape: new(employee_to_holidays) + get_scored_solution(solution)."""
+
+    def __init__(self, n_days, employees, start_weekday=0, holidays=()):
+        self._e = ScheduleChains(n_days, employees, start_weekday=start_weekday, holidays=holidays)
+
+    def get_scored_solution(self, date_to_employee):
+        self._e.set_chains(date_to_employee)
+        hard, soft, _ = self._e.score_full(0)
+        return ScheduleScore(float(hard), float(soft)), np.asarray(date_to_employee)

@@ -177,6 +177,98 @@ int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain, const void* 
 int32_t cs_nq_chain_device_ptr(cs_nq_handle* h, uint32_t chain, void** dptr,
                                uint32_t* stride_elems);
 
+/* ------------------------------------------------------------------ employee scheduling */
+/* One employee per calendar day (examples/employee-scheduling/src/lib.rs:127-146).  A solution
+ * is the reference's `date_to_employee`: n_days + 1 int64 employee ids -- the generator pushes
+ * one phantom slot past end_date (lib.rs:405-412) that is stored and returned untouched but
+ * never scored or moved.  Scores are the reference's (hard, soft) pair (lib.rs:239-249;
+ * OrderedFloat<f64> holding integers only) as two int64. */
+typedef struct cs_es_handle cs_es_handle;
+
+#define CS_ES_MAX_DAYS 64u
+#define CS_ES_CHANGE 0u /* ChangeDay: a = day, b = index into the sorted employee table, lib.rs:466-470 */
+#define CS_ES_SWAP 1u   /* SwapDays: a < b days, lib.rs:471-478 */
+
+typedef struct cs_es_config {
+    uint32_t n_days;         /* D = end_date - start_date + 1, 1..CS_ES_MAX_DAYS */
+    uint32_t n_employees;    /* E, 1..65535 */
+    uint32_t start_weekday;  /* weekday of start_date, 0 = Monday .. 6 = Sunday */
+    uint32_t n_chains;
+    uint32_t chain_offset;
+    uint32_t trace_capacity;
+    uint64_t seed;
+    int32_t device;
+    uint32_t reserved;
+} cs_es_config;
+
+typedef struct cs_es_move {
+    uint32_t kind; /* CS_ES_CHANGE / CS_ES_SWAP */
+    uint32_t a;
+    uint32_t b;
+} cs_es_move;
+
+typedef struct cs_es_step_stats {
+    uint64_t moves_scored;
+    uint64_t steps_accepted;
+    int64_t best_hard; /* lexicographically best (hard, soft) over this handle's chains */
+    int64_t best_soft;
+    uint32_t best_chain;
+    uint32_t chains_at_best;  /* hard == 0 && soft == 0 */
+    uint32_t chains_feasible; /* hard == 0 */
+    float device_ms;
+    uint32_t kernel_launches;
+} cs_es_step_stats;
+
+/* get_ils / ScheduleSolutionScoreCalculator::new (lib.rs:57-117, :255-259): employee ids (any
+ * order, unique; kept sorted like the reference's BTreeSet) and the holiday table as n_hol
+ * (employee id, day index from start_date) pairs.  A holiday outside [0, n_days) is
+ * CS_ERR_INVALID_ARG (the reference unwrap()s a None there, lib.rs:275). */
+int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee_ids, const int64_t* hol_emp,
+                     const int64_t* hol_day, uint64_t n_hol, cs_es_handle** out);
+int32_t cs_es_destroy(cs_es_handle* h);
+const char* cs_es_last_error(const cs_es_handle* h);
+int32_t cs_es_set_stream(cs_es_handle* h, void* cuda_stream);
+/* ScheduleInitialSolutionGenerator::generate_initial_solution, lib.rs:400-420 */
+int32_t cs_es_init_random(cs_es_handle* h);
+/* rows: int64 [count][n_days + 1] employee ids */
+int32_t cs_es_set_chains(cs_es_handle* h, uint32_t first_chain, uint32_t count, const int64_t* rows);
+int32_t cs_es_get_chains(cs_es_handle* h, uint32_t first_chain, uint32_t count, int64_t* rows);
+int32_t cs_es_get_scores(cs_es_handle* h, int64_t* hard, int64_t* soft);
+int32_t cs_es_get_status(cs_es_handle* h, uint32_t* status);
+/* ScheduleSolutionScoreCalculator::get_scored_solution, lib.rs:261-375: device full re-score by
+ * the reference's own loops over the day vector (not the mask/tally formulation).
+ * terms (optional) = H1..H4, S1..S4. */
+int32_t cs_es_score_full(cs_es_handle* h, uint32_t chain, int64_t* hard, int64_t* soft,
+                         int64_t terms[8]);
+/* exact (dhard, dsoft) of explicit moves; identity moves report INT64_MAX in both */
+int32_t cs_es_eval_moves(cs_es_handle* h, uint32_t chain, const cs_es_move* moves, uint64_t n_moves,
+                         int64_t* dhard, int64_t* dsoft);
+/* ScheduleMoveProposer::iter_local_moves precedent (lib.rs:511-559): the FULL neighbourhood,
+ * change moves (day outer, employee index inner) then swaps (a<b), identity moves skipped. */
+int32_t cs_es_enumerate(cs_es_handle* h, uint32_t chain, cs_es_move* moves, uint64_t cap,
+                        uint64_t* n_out);
+/* production scan, every candidate in enumeration order INCLUDING identities (INT64_MAX):
+ * n_days*n_employees change entries then n_days*(n_days-1)/2 swap entries */
+int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, int64_t* dhard, int64_t* dsoft,
+                                   uint64_t cap, uint64_t* n_out);
+/* hot path: enumerate change + swap moves, delta-score the 8 constraints, lexicographic
+ * (hard, soft, move id) argmin, accept (local_search.rs:315-335) */
+int32_t cs_es_step(cs_es_handle* h, uint32_t n_steps, cs_es_step_stats* stats);
+/* LocalSearch::execute, local_search.rs:301-342 */
+int32_t cs_es_local_search(cs_es_handle* h, uint64_t allow_no_improvement_for,
+                           uint64_t max_iterations, cs_es_step_stats* stats);
+int32_t cs_es_get_best_chains(cs_es_handle* h, uint32_t first_chain, uint32_t count, int64_t* rows,
+                              int64_t* best_hard, int64_t* best_soft);
+int32_t cs_es_local_search_one(cs_es_handle* h, const int64_t* start,
+                               uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                               int64_t* best, int64_t* best_hard, int64_t* best_soft);
+int32_t cs_es_get_trace(cs_es_handle* h, uint32_t chain, cs_es_move* moves, int64_t* hard_after,
+                        int64_t* soft_after, uint64_t cap, uint64_t* n_out);
+int32_t cs_es_best(cs_es_handle* h, int64_t* rows, int64_t* hard, int64_t* soft, uint32_t* chain);
+/* device int64: (hard << 48) | (soft << 32) | global chain id */
+int32_t cs_es_best_key_device_ptr(cs_es_handle* h, void** dptr);
+int32_t cs_es_chain_device_ptr(cs_es_handle* h, uint32_t chain, void** dptr, uint32_t* n_slots);
+
 #ifdef __cplusplus
 }
 #endif

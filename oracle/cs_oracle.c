@@ -371,6 +371,17 @@ int orc_es_score(const int64_t* a, int64_t D, int start_weekday, const int64_t* 
     return 0;
 }
 
+/* examples/employee-scheduling/src/lib.rs:404-419: one uniformly random employee per slot,
+ * n_slots = D + 1 (the loop pushes a phantom slot past end_date before it breaks).
+ * `choose` restated as employees[mulhi(u32, E)] over Philox purpose 0, draw s for slot s. */
+void orc_es_init(uint64_t seed, uint32_t chain, int64_t n_slots, const int64_t* employees,
+                 int64_t E, int64_t* out) {
+    for (int64_t s = 0; s < n_slots; ++s) {
+        const uint32_t u = orc_philox_draw(seed, chain, 0u, (uint64_t)s);
+        out[s] = employees[(int64_t)(((uint64_t)u * (uint64_t)E) >> 32)];
+    }
+}
+
 static int es_apply(int64_t* cand, const int64_t* employees, int kind, int64_t x, int64_t y) {
     if (kind == ORC_ES_CHANGE) { /* lib.rs:466-470 */
         if (cand[x] == employees[y]) return 0;

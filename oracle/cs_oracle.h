@@ -98,6 +98,10 @@ int orc_es_score(const int64_t* a, int64_t D, int start_weekday, const int64_t* 
 int orc_es_score_terms(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
                        const int64_t* hol_day, int64_t n_hol, int64_t out[8]);
 
+/* generate_initial_solution, examples/employee-scheduling/src/lib.rs:400-420 (n_slots = D+1) */
+void orc_es_init(uint64_t seed, uint32_t chain, int64_t n_slots, const int64_t* employees,
+                 int64_t E, int64_t* out);
+
 enum { ORC_ES_CHANGE = 0, ORC_ES_SWAP = 1 };
 /* Clone + full re-score of explicit moves. CHANGE: a[x[k]] = employees[y[k]] (y = index into
  * the employee id table); SWAP: exchange days x[k], y[k].  Identity => INT64_MAX in both. */

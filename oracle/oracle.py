@@ -179,6 +179,14 @@ def es_score(a, start_weekday=0, holidays=None):
 ES_CHANGE, ES_SWAP = 0, 1
 
 
+def es_init(seed, chain, n_slots, employees):
+    employees = _i64(employees)
+    out = np.zeros(n_slots, dtype=np.int64)
+    lib().orc_es_init(U64(seed), C.c_uint32(chain), I64(n_slots), _p(employees),
+                      I64(len(employees)), _p(out))
+    return out
+
+
 def es_eval_moves(a, employees, x, y, kind, start_weekday=0, holidays=None):
     a, employees, x, y = _i64(a), _i64(employees), _i64(x), _i64(y)
     he, hd = _hol(holidays)

@@ -1,0 +1,224 @@
+"""GPU parity suite for the employee-scheduling path: mask/tally delta kernels (through the
+C ABI) against the CPU oracle's clone + full re-score of
+examples/employee-scheduling/src/lib.rs:261-375.  Bit-exact (scores hold integers only)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import constraint_solver_b200 as cs
+from constraint_solver_b200 import _lib as L
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _instances():
+    """(D, employee ids, start_weekday, holidays) covering every window-length regime."""
+    rng = np.random.default_rng(77)
+    out = []
+    for D, E, wd in [(1, 1, 0), (2, 2, 3), (5, 3, 6), (7, 2, 0), (8, 4, 5), (9, 3, 4), (13, 5, 2),
+                     (14, 2, 0), (15, 7, 1), (28, 50, 0), (31, 7, 0), (56, 9, 5), (64, 3, 6),
+                     (64, 70, 0), (30, 1, 2)]:
+        ids = np.sort(rng.choice(np.arange(0, 5 * E + 3), size=E, replace=False)).astype(np.int64)
+        nh = int(rng.integers(0, 2 * E + 1))
+        hol = sorted({(int(ids[rng.integers(0, E)]), int(rng.integers(0, D))) for _ in range(nh)})
+        out.append((D, ids, wd, hol))
+    return out
+
+
+def _full_move_list(D, E):
+    kind = [0] * (D * E) + [1] * (D * (D - 1) // 2)
+    x = [d for d in range(D) for _ in range(E)] + [a for a in range(D) for b in range(a + 1, D)]
+    y = [e for _ in range(D) for e in range(E)] + [b for a in range(D) for b in range(a + 1, D)]
+    return np.array(kind), np.array(x), np.array(y)
+
+
+def _oracle_deltas(a, ids, wd, hol):
+    D, E = len(a), len(ids)
+    kind, x, y = _full_move_list(D, E)
+    dh = np.empty(len(kind), dtype=np.int64)
+    ds = np.empty(len(kind), dtype=np.int64)
+    for k in (0, 1):
+        m = kind == k
+        if m.any():
+            h, s = orc.es_eval_moves(a, ids, x[m], y[m], k, wd, hol)
+            dh[m], ds[m] = h, s
+    return dh, ds
+
+
+def test_golden_vectors_on_device(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "es_kat.json")))
+    for case in g["cases"]:
+        a = np.array(case["a"], dtype=np.int64)
+        ids = np.arange(7)
+        with cs.ScheduleChains(len(a), ids, start_weekday=g["start_weekday"], holidays=case["holidays"]) as e:
+            e.set_chains(a)
+            hard, soft, terms = e.score_full(0)  # reference-loop kernel
+            assert (hard, soft) == (case["hard"], case["soft"]) and terms == case["terms"]
+            h2, s2 = e.scores()  # mask / tally formulation
+            assert (int(h2[0]), int(s2[0])) == (case["hard"], case["soft"])
+
+
+def test_init_matches_host_philox_mirror_and_scores():
+    for D, ids, wd, hol in _instances()[::3]:
+        with cs.ScheduleChains(D, ids, start_weekday=wd, holidays=hol, n_chains=4, seed=5, chain_offset=9) as e:
+            e.init_random()
+            rows = e.get_chains()
+            hard, soft = e.scores()
+            for k in range(4):
+                assert np.array_equal(rows[k], orc.es_init(5, 9 + k, D + 1, ids))
+                assert orc.es_score(rows[k][:D], wd, hol) == (int(hard[k]), int(soft[k]))
+                assert e.score_full(k)[:2] == (int(hard[k]), int(soft[k]))
+
+
+def test_every_delta_equals_full_rescore_difference():
+    rng = np.random.default_rng(123)
+    for D, ids, wd, hol in _instances():
+        E = len(ids)
+        states = [ids[rng.integers(0, E, size=D + 1)] for _ in range(3)]
+        states.append(np.full(D + 1, ids[0]))                      # one employee everywhere
+        states.append(ids[np.arange(D + 1) % E])                   # round robin
+        states.append(ids[(np.arange(D + 1) // 2) % E])            # pairs
+        with cs.ScheduleChains(D, ids, start_weekday=wd, holidays=hol, n_chains=len(states)) as e:
+            e.set_chains(np.stack(states))
+            hard, soft = e.scores()
+            for k, a in enumerate(states):
+                ref_h, ref_s = _oracle_deltas(a[:D], ids, wd, hol)
+                dev_h, dev_s = e.neighbourhood_deltas(k)
+                bad = np.nonzero((dev_h != ref_h) | (dev_s != ref_s))[0]
+                assert bad.size == 0, (D, E, wd, k, bad[:6], dev_h[bad[:6]], ref_h[bad[:6]],
+                                       dev_s[bad[:6]], ref_s[bad[:6]])
+                assert orc.es_score(a[:D], wd, hol) == (int(hard[k]), int(soft[k]))
+                assert e.score_full(k)[:2] == (int(hard[k]), int(soft[k]))
+                assert e.score_full(k)[2] == orc.es_score_terms(a[:D], wd, hol).tolist()
+
+
+def test_eval_moves_hook_and_enumerate():
+    rng = np.random.default_rng(4)
+    D, ids, wd, hol = 31, np.arange(7), 0, [(0, 0), (0, 1), (3, 3)]
+    a = ids[rng.integers(0, 7, size=D + 1)]
+    with cs.ScheduleChains(D, ids, start_weekday=wd, holidays=hol) as e:
+        e.set_chains(a)
+        mv = e.enumerate(0)
+        ref_h, ref_s = _oracle_deltas(a[:D], ids, wd, hol)
+        assert len(mv) == int((ref_h != orc.INT64_MAX).sum())
+        dh, ds = e.eval_moves(mv["kind"], mv["a"], mv["b"], 0)
+        keep = ref_h != orc.INT64_MAX
+        assert np.array_equal(dh, ref_h[keep]) and np.array_equal(ds, ref_s[keep])
+        # identity moves on both sides
+        dh, ds = e.eval_moves([0] * D, np.arange(D), a[:D], 0)
+        assert (dh == orc.INT64_MAX).all() and (ds == orc.INT64_MAX).all()
+
+
+def test_step_trace_replays_and_matches_oracle_argmin():
+    rng = np.random.default_rng(8)
+    for D, ids, wd, hol in [(14, np.arange(4), 0, [(1, 2)]), (28, np.arange(6), 0, [(0, 5), (3, 6)]),
+                            (31, np.arange(7), 0, [])]:
+        E = len(ids)
+        starts = np.stack([ids[rng.integers(0, E, size=D + 1)] for _ in range(3)])
+        with cs.ScheduleChains(D, ids, start_weekday=wd, holidays=hol, n_chains=3, trace_capacity=8) as e:
+            e.set_chains(starts)
+            e.step(5)
+            after = e.get_chains()
+            hard, soft = e.scores()
+            for k in range(3):
+                mv, th, ts, total = e.trace(k)
+                a = starts[k][:D].copy()
+                for m, h, s in zip(mv, th, ts):
+                    dh, ds = _oracle_deltas(a, ids, wd, hol)
+                    key = dh.astype(object) * 100000 + ds.astype(object)
+                    best = int(np.argmin(np.where(dh == orc.INT64_MAX, 10**30, key)))
+                    kind, x, y = _full_move_list(D, E)
+                    assert (int(m["kind"]), int(m["a"]), int(m["b"])) == (int(kind[best]), int(x[best]), int(y[best]))
+                    if m["kind"] == cs.scheduling.CHANGE:
+                        a[m["a"]] = ids[m["b"]]
+                    else:
+                        a[m["a"]], a[m["b"]] = a[m["b"]], a[m["a"]]
+                    assert orc.es_score(a, wd, hol) == (int(h), int(s))
+                assert np.array_equal(a, after[k][:D])
+                assert after[k][D] == starts[k][D]  # phantom slot untouched
+                assert orc.es_score(a, wd, hol) == (int(hard[k]), int(soft[k]))
+
+
+def test_local_search_matches_oracle_execute():
+    rng = np.random.default_rng(21)
+    for D, E, allow, iters in [(14, 4, 3, 40), (21, 5, 20, 30), (31, 7, 20, 25), (10, 3, 1, 10)]:
+        ids = np.arange(E) * 3 + 1
+        hol = [(int(ids[0]), 2), (int(ids[E - 1]), D - 1)]
+        start = ids[rng.integers(0, E, size=D + 1)]
+        ref = orc.es_local_search(start[:D], ids, 0, hol, allow_no_improvement_for=allow,
+                                  max_iterations=iters, trace_cap=256)
+        with cs.ScheduleChains(D, ids, holidays=hol, n_chains=2, trace_capacity=256) as e:
+            e.set_chains(np.stack([start, start]))
+            e.local_search(allow, iters)
+            mv, th, ts, total = e.trace(1)
+            assert total == ref["steps"]
+            assert np.array_equal(mv["kind"], ref["trace_kind"]) and np.array_equal(mv["a"], ref["trace_x"])
+            assert np.array_equal(mv["b"], ref["trace_y"])
+            assert np.array_equal(th, ref["trace_hard"]) and np.array_equal(ts, ref["trace_soft"])
+            best, bh, bs = e.get_best_chains()
+            assert (int(bh[1]), int(bs[1])) == (ref["best_hard"], ref["best_soft"])
+            assert np.array_equal(best[1][:D], ref["best"])
+            assert np.array_equal(e.get_chains()[1][:D], ref["current"])
+            one_best, oh, os_ = e.local_search_one(start, allow, iters)
+            assert (oh, os_) == (ref["best_hard"], ref["best_soft"]) and np.array_equal(one_best[:D], ref["best"])
+
+
+def test_errors_and_edge_cases():
+    lib = cs.load()
+    with pytest.raises(cs.CsError) as err:  # holiday outside the range: the reference panics (lib.rs:275)
+        cs.ScheduleChains(10, [0, 1], holidays=[(0, 10)])
+    assert err.value.status == L.CS_ERR_INVALID_ARG
+    with pytest.raises(cs.CsError) as err:
+        cs.ScheduleChains(65, [0, 1])
+    assert err.value.status == L.CS_ERR_UNSUPPORTED
+    with pytest.raises(cs.CsError):
+        cs.ScheduleChains(10, [3, 3])  # duplicate employee ids
+    with cs.ScheduleChains(10, [5, 9]) as e:
+        with pytest.raises(cs.CsError):
+            e.step(1)  # no solution yet
+        with pytest.raises(cs.CsError):
+            e.set_chains(np.full(11, 4))  # unknown employee id
+        e.set_chains(np.array([5, 9] * 5 + [5]))
+        st = e.step(1)
+        assert st.moves_scored == 10 * 1 + 25  # 10 non-identity changes + 25 swaps of unequal days
+    with cs.ScheduleChains(6, [1]) as e:  # single employee: every move is an identity
+        e.set_chains(np.ones(7, dtype=np.int64))
+        st = e.step(2)
+        assert st.steps_accepted == 0 and e.status()[0] == L.CHAIN_EMPTY
+
+
+def test_baseline_config_sizes_run_and_replay():
+    """BASELINE configs 3 and 4 at full size (reference-faithful one slot per day): trace
+    replay through the oracle scorer + device re-score agreement."""
+    rng = np.random.default_rng(1)
+    for D, E, nhol in [(28, 50, 2), (56, 2000, 4)]:
+        ids = np.arange(E)
+        hol = sorted({(int(e), int(d)) for e in range(E) for d in rng.choice(D, size=nhol, replace=False)})
+        with cs.ScheduleChains(D, ids, holidays=hol, n_chains=6, seed=42, trace_capacity=4) as e:
+            e.init_random()
+            rows0 = e.get_chains()
+            st = e.step(3)
+            assert st.steps_accepted == 18
+            hard, soft = e.scores()
+            rows1 = e.get_chains()
+            for k in range(6):
+                mv, th, ts, total = e.trace(k)
+                a = rows0[k][:D].copy()
+                for m, h, s in zip(mv, th, ts):
+                    if m["kind"] == 0:
+                        a[m["a"]] = ids[m["b"]]
+                    else:
+                        a[m["a"]], a[m["b"]] = a[m["b"]], a[m["a"]]
+                    assert orc.es_score(a, 0, hol) == (int(h), int(s))
+                assert np.array_equal(a, rows1[k][:D])
+                assert e.score_full(k)[:2] == (int(hard[k]), int(soft[k]))
+            # sampled deltas at full size
+            a = rows1[0][:D]
+            x = rng.integers(0, D, size=200)
+            y = rng.integers(0, E, size=200)
+            dh, ds = e.eval_moves([0] * 200, x, y, 0)
+            rh, rs = orc.es_eval_moves(a, ids, x, y, orc.ES_CHANGE, 0, hol)
+            assert np.array_equal(dh, rh) and np.array_equal(ds, rs)
