@@ -454,7 +454,7 @@ __global__ void es_step_kernel(EsParams p) {
         unsigned int steps = steps0, status = 0;
 
         for (unsigned long long it = 0; it < p.max_steps; ++it) {
-            if (hard == 0 && soft == 0) {  // is_best, lib.rs:245-249
+            if (hard == 0 && soft == 0 && !p.dump_h) {  // is_best, lib.rs:245-249
                 status = 1;
                 best_h = 0;
                 best_s = 0;

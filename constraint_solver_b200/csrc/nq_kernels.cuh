@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
         }
 
         for (unsigned long long it = 0; it < p.max_steps; ++it) {
-            if (score == 0) {  // is_best, local_search.rs:311-314 (returns current)
+            if (score == 0 && !p.dump) {  // is_best, local_search.rs:311-314 (returns current)
                 status = 1;
                 if (p.ls_mode && best_score != 0) best_dirty = true;
                 best_score = 0;
