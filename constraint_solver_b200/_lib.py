@@ -22,6 +22,8 @@ CS_ERR_UNSUPPORTED = -6
 
 CS_NQ_SWAP, CS_NQ_CHANGE = 0, 1
 CS_NQ_MAX_N_SMEM = 16384
+CS_NQ_MAX_N = 1_000_000
+CS_NQ_FLAG_GLOBAL = 1
 CHAIN_RUNNING, CHAIN_BEST, CHAIN_STALLED, CHAIN_EMPTY = 0, 1, 2, 3
 PHILOX_INIT, PHILOX_PERTURB, PHILOX_ACCEPT, PHILOX_HOLIDAYS = 0, 1, 2, 3
 
@@ -60,6 +62,7 @@ class CsNqConfig(C.Structure):
         ("seed", C.c_uint64),
         ("device", C.c_int32),
         ("neighbourhood", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -129,6 +132,10 @@ SIGNATURES = {
     "cs_nq_best_key_device_ptr": (C.c_int32, [_VP, _P(_VP)]),
     "cs_nq_set_chain_u16_device": (C.c_int32, [_VP, C.c_uint32, _VP]),
     "cs_nq_chain_device_ptr": (C.c_int32, [_VP, C.c_uint32, _P(_VP), _P(C.c_uint32)]),
+    "cs_nq_set_partition": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "cs_nq_part_scan": (C.c_int32, [_VP]),
+    "cs_nq_part_key_device_ptr": (C.c_int32, [_VP, _P(_VP)]),
+    "cs_nq_part_apply": (C.c_int32, [_VP, _P(CsStepStats)]),
     "cs_es_create": (C.c_int32, [_P(CsEsConfig), _VP, _VP, _VP, C.c_uint64, _P(_VP)]),
     "cs_es_destroy": (C.c_int32, [_VP]),
     "cs_es_last_error": (C.c_char_p, [_VP]),

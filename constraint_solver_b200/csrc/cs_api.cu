@@ -10,6 +10,7 @@
 
 #include "../../include/cs_b200.h"
 #include "nq_kernels.cuh"
+#include "nq_big.cuh"
 #include "philox.cuh"
 
 using namespace csb;
@@ -130,6 +131,16 @@ struct cs_nq_handle {
     int* d_bad = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;  // chain scores valid
+    // big-board (global-memory) mode: one instance, optional neighbourhood partition
+    bool is_big = false;
+    NqBig big{};
+    unsigned int* d_best_rows32 = nullptr;
+    NqBigStep* d_bstep = nullptr;
+    NqBigStep* h_bstep = nullptr;       // pinned
+    long long* h_key = nullptr;         // pinned
+    unsigned long long* h_scored = nullptr;  // pinned
+    uint32_t part = 0, parts = 1;
+    unsigned long long ls_no_improve = 0;
     std::string err;
 };
 
@@ -170,6 +181,19 @@ void nq_free(cs_nq_handle* h) {
     cudaFree(h->d_stats);
     cudaFree(h->d_stage);
     cudaFree(h->d_bad);
+    if (h->is_big) {
+        cudaFree(h->big.rows);
+        cudaFree(h->big.c);
+        cudaFree(h->big.R);
+        cudaFree(h->big.D1);
+        cudaFree(h->big.D2);
+        cudaFree(h->big.score);
+        cudaFree(h->d_best_rows32);
+        cudaFree(h->d_bstep);
+        if (h->h_bstep) cudaFreeHost(h->h_bstep);
+        if (h->h_key) cudaFreeHost(h->h_key);
+        if (h->h_scored) cudaFreeHost(h->h_scored);
+    }
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->h_totals) cudaFreeHost(h->h_totals);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -274,12 +298,17 @@ void nq_download(cs_nq_handle* h, const uint16_t* src, uint32_t first, uint32_t 
 
 }  // namespace
 
+#include "nq_big_api.cuh"
+
 extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
     if (!cfg || !out) return CS_ERR_INVALID_ARG;
     *out = nullptr;
     if (cfg->n < 1 || cfg->n_chains < 1 || cfg->neighbourhood > CS_NQ_CHANGE)
         return CS_ERR_INVALID_ARG;
-    if (cfg->n > CS_NQ_MAX_N_SMEM) return CS_ERR_UNSUPPORTED;
+    if (cfg->n > CS_NQ_MAX_N) return CS_ERR_UNSUPPORTED;
+    const bool big = cfg->n > CS_NQ_MAX_N_SMEM || (cfg->flags & CS_NQ_FLAG_GLOBAL);
+    // the L2-resident path holds one instance per handle and scores the swap neighbourhood
+    if (big && (cfg->n_chains != 1 || cfg->neighbourhood != CS_NQ_SWAP)) return CS_ERR_UNSUPPORTED;
     if ((uint64_t)cfg->chain_offset + cfg->n_chains > 0xffffffffull) return CS_ERR_INVALID_ARG;
     int ndev = cs_device_count();
     if (ndev <= 0) return CS_ERR_NO_DEVICE;
@@ -292,12 +321,34 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
     if (!h) return CS_ERR_OOM;
     h->cfg = *cfg;
     h->device = dev;
+    h->is_big = big;
     const int32_t rc = guarded(h, [&] {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, dev));
         h->sm_count = prop.multiProcessorCount;
         const int n = (int)cfg->n;
         h->n_pad = round_up(n, NQ_PAD);
+        if (big) {
+            CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            h->own_stream = true;
+            CU(cudaMalloc(&h->d_st, sizeof(NqChainState)));
+            if (cfg->trace_capacity)
+                CU(cudaMalloc(&h->d_trace, cfg->trace_capacity * sizeof(NqTraceEntry)));
+            CU(cudaMalloc(&h->d_totals, 2 * sizeof(unsigned long long)));
+            CU(cudaMalloc(&h->d_stats, sizeof(NqStats)));
+            CU(cudaMalloc(&h->d_bad, sizeof(int)));
+            CU(cudaMallocHost(&h->h_stats, sizeof(NqStats)));
+            CU(cudaMallocHost(&h->h_totals, 2 * sizeof(unsigned long long)));
+            h->stage_elems = n;
+            CU(cudaMalloc(&h->d_stage, h->stage_elems * sizeof(int64_t)));
+            CU(cudaEventCreate(&h->ev0));
+            CU(cudaEventCreate(&h->ev1));
+            nqb_alloc(h);
+            nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, 0, 1);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(h->stream));
+            return;
+        }
         h->smem = nq_smem_bytes(h->n_pad);
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin,
                 "board does not fit the shared-memory chain kernel on this device");
@@ -374,6 +425,14 @@ extern "C" int32_t cs_nq_set_stream(cs_nq_handle* h, void* s) {
 
 extern "C" int32_t cs_nq_init_random(cs_nq_handle* h) {
     return guarded(h, [&] {
+        if (h->is_big) {
+            nqb_init_kernel<<<1, 1, 0, h->stream>>>(h->big.rows, (int)h->cfg.n, h->n_pad, h->cfg.seed,
+                                                    h->cfg.chain_offset);
+            CU(cudaGetLastError());
+            nqb_rebuild(h, true);
+            h->scored = true;
+            return;
+        }
         const int nc = (int)h->cfg.n_chains;
         nq_init_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(h->d_rows, h->d_st, (int)h->cfg.n,
                                                               h->n_pad, nc, h->cfg.seed,
@@ -391,6 +450,12 @@ extern "C" int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first, uint32_t co
     return guarded(h, [&] {
         REQUIRE(rows, "rows is NULL");
         nq_check_range(h, first, count);
+        if (h->is_big) {
+            nqb_upload(h, rows);
+            nqb_rebuild(h, true);
+            h->scored = true;
+            return;
+        }
         nq_upload(h, first, count, rows);
         nq_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first,
                                                                           (int)count);
@@ -411,6 +476,10 @@ extern "C" int32_t cs_nq_get_chains(cs_nq_handle* h, uint32_t first, uint32_t co
     return guarded(h, [&] {
         REQUIRE(rows, "rows is NULL");
         nq_check_range(h, first, count);
+        if (h->is_big) {
+            nqb_download(h, h->big.rows, rows);
+            return;
+        }
         nq_download(h, h->d_rows, first, count, rows);
     });
 }
@@ -419,7 +488,10 @@ extern "C" int32_t cs_nq_get_best_chains(cs_nq_handle* h, uint32_t first, uint32
                                          int64_t* rows, int64_t* best_scores) {
     return guarded(h, [&] {
         nq_check_range(h, first, count);
-        if (rows) nq_download(h, h->d_best_rows, first, count, rows);
+        if (rows) {
+            if (h->is_big) nqb_download(h, h->d_best_rows32, rows);
+            else nq_download(h, h->d_best_rows, first, count, rows);
+        }
         if (best_scores) {
             std::vector<NqChainState> st(count);
             CU(cudaMemcpyAsync(st.data(), h->d_st + first, count * sizeof(NqChainState),
@@ -460,8 +532,11 @@ extern "C" int32_t cs_nq_score_full(cs_nq_handle* h, uint32_t chain, int64_t* sc
         CU(cudaMemsetAsync(d_pairs, 0, sizeof(unsigned long long), h->stream));
         const int n = (int)h->cfg.n;
         const int grid = n < 2048 ? (n > 0 ? n : 1) : 2048;
-        nq_pair_score_kernel<<<grid, 256, 0, h->stream>>>(h->d_rows + (size_t)chain * h->n_pad, n,
-                                                          d_pairs);
+        if (h->is_big)
+            nq_pair_score_kernel<unsigned int><<<grid, 256, 0, h->stream>>>(h->big.rows, n, d_pairs);
+        else
+            nq_pair_score_kernel<uint16_t><<<grid, 256, 0, h->stream>>>(
+                h->d_rows + (size_t)chain * h->n_pad, n, d_pairs);
         CU(cudaGetLastError());
         unsigned long long pairs = 0;
         CU(cudaMemcpyAsync(&pairs, d_pairs, sizeof pairs, cudaMemcpyDeviceToHost, h->stream));
@@ -491,9 +566,15 @@ extern "C" int32_t cs_nq_eval_moves(cs_nq_handle* h, uint32_t chain, uint32_t ki
         try {
             CU(cudaMemcpyAsync(d_moves, moves, n_moves * sizeof(uint2), cudaMemcpyHostToDevice,
                                h->stream));
-            NqParams p = nq_params(h, 0, (int)h->cfg.n_chains);
-            nq_eval_kernel<<<1, h->threads, h->smem, h->stream>>>(p, (int)chain, (int)kind, d_moves,
-                                                                  n_moves, d_delta);
+            if (h->is_big) {
+                REQUIRE(kind == CS_NQ_SWAP, "the big-board path scores swap moves only");
+                nqb_eval_kernel<<<nqb_grid(h, (long long)n_moves), 256, 0, h->stream>>>(
+                    h->big, d_moves, n_moves, d_delta);
+            } else {
+                NqParams p = nq_params(h, 0, (int)h->cfg.n_chains);
+                nq_eval_kernel<<<1, h->threads, h->smem, h->stream>>>(p, (int)chain, (int)kind,
+                                                                      d_moves, n_moves, d_delta);
+            }
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(delta, d_delta, n_moves * sizeof(long long), cudaMemcpyDeviceToHost,
                                h->stream));
@@ -515,7 +596,8 @@ extern "C" int32_t cs_nq_enumerate(cs_nq_handle* h, uint32_t chain, cs_move* mov
         REQUIRE(n_out, "n_out is NULL");
         const uint32_t n = h->cfg.n;
         std::vector<int64_t> rows(n);
-        nq_download(h, h->d_rows, chain, 1, rows.data());
+        if (h->is_big) nqb_download(h, h->big.rows, rows.data());
+        else nq_download(h, h->d_rows, chain, 1, rows.data());
         uint64_t k = 0;
         if (h->cfg.neighbourhood == CS_NQ_SWAP) {
             for (uint32_t i = 0; i < n; ++i)
@@ -551,12 +633,16 @@ extern "C" int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, i
         CU(cudaMalloc(&d_dump, cnt * sizeof(long long)));
         try {
             CU(cudaMemsetAsync(d_dump, 0x7f, cnt * sizeof(long long), h->stream));
-            NqParams p = nq_params(h, (int)chain, 1);
-            p.max_steps = 1;
-            p.dump = d_dump;
-            CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-            nq_step_kernel<NQ_TI><<<1, h->threads, h->smem, h->stream>>>(p);
-            CU(cudaGetLastError());
+            if (h->is_big) {
+                nqb_enqueue_scan(h, nqb_is_perm(h), d_dump);
+            } else {
+                NqParams p = nq_params(h, (int)chain, 1);
+                p.max_steps = 1;
+                p.dump = d_dump;
+                CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+                nq_step_kernel<NQ_TI><<<1, h->threads, h->smem, h->stream>>>(p);
+                CU(cudaGetLastError());
+            }
             CU(cudaMemcpyAsync(delta, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost,
                                h->stream));
             CU(cudaStreamSynchronize(h->stream));
@@ -570,14 +656,16 @@ extern "C" int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, i
 
 extern "C" int32_t cs_nq_step(cs_nq_handle* h, uint32_t n_steps, cs_step_stats* stats) {
     return guarded(h, [&] {
-        nq_run(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0, stats);
+        if (h->is_big) nqb_run(h, n_steps, 0, 0, stats);
+        else nq_run(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0, stats);
     });
 }
 
 extern "C" int32_t cs_nq_local_search(cs_nq_handle* h, uint64_t allow, uint64_t max_iterations,
                                       cs_step_stats* stats) {
     return guarded(h, [&] {
-        nq_run(h, 0, (int)h->cfg.n_chains, max_iterations, allow, 1, stats);
+        if (h->is_big) nqb_run(h, max_iterations, allow, 1, stats);
+        else nq_run(h, 0, (int)h->cfg.n_chains, max_iterations, allow, 1, stats);
     });
 }
 
@@ -586,13 +674,21 @@ extern "C" int32_t cs_nq_local_search_one(cs_nq_handle* h, const int64_t* start,
                                           int64_t* best_score) {
     return guarded(h, [&] {
         REQUIRE(start, "start is NULL");
-        nq_upload(h, 0, 1, start);
-        nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, 0, 1);
-        CU(cudaGetLastError());
-        nq_rescore(h, 0, h->scored ? 1 : (int)h->cfg.n_chains);
-        h->scored = true;
-        nq_run(h, 0, 1, max_iterations, allow, 1, nullptr);
-        if (best) nq_download(h, h->d_best_rows, 0, 1, best);
+        if (h->is_big) {
+            nqb_upload(h, start);
+            nqb_rebuild(h, true);
+            h->scored = true;
+            nqb_run(h, max_iterations, allow, 1, nullptr);
+            if (best) nqb_download(h, h->d_best_rows32, best);
+        } else {
+            nq_upload(h, 0, 1, start);
+            nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, 0, 1);
+            CU(cudaGetLastError());
+            nq_rescore(h, 0, h->scored ? 1 : (int)h->cfg.n_chains);
+            h->scored = true;
+            nq_run(h, 0, 1, max_iterations, allow, 1, nullptr);
+            if (best) nq_download(h, h->d_best_rows, 0, 1, best);
+        }
         if (best_score) {
             NqChainState st;
             CU(cudaMemcpyAsync(&st, h->d_st, sizeof st, cudaMemcpyDeviceToHost, h->stream));
@@ -633,7 +729,10 @@ extern "C" int32_t cs_nq_best(cs_nq_handle* h, int64_t* rows, int64_t* score, ui
         CU(cudaStreamSynchronize(h->stream));
         if (score) *score = h->h_stats->best_score;
         if (chain) *chain = h->h_stats->best_chain;
-        if (rows) nq_download(h, h->d_rows, h->h_stats->best_chain, 1, rows);
+        if (rows) {
+            if (h->is_big) nqb_download(h, h->big.rows, rows);
+            else nq_download(h, h->d_rows, h->h_stats->best_chain, 1, rows);
+        }
     });
 }
 
@@ -649,6 +748,7 @@ extern "C" int32_t cs_nq_chain_device_ptr(cs_nq_handle* h, uint32_t chain, void*
     return guarded(h, [&] {
         nq_check_range(h, chain, 1);
         REQUIRE(dptr, "dptr is NULL");
+        REQUIRE(!h->is_big, "big-board rows are uint32; use cs_nq_get_chains");
         *dptr = (void*)(h->d_rows + (size_t)chain * h->n_pad);
         if (stride_elems) *stride_elems = (uint32_t)h->n_pad;
     });
@@ -659,6 +759,7 @@ extern "C" int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain,
     return guarded(h, [&] {
         nq_check_range(h, chain, 1);
         REQUIRE(d_rows_u16, "d_rows_u16 is NULL");
+        REQUIRE(!h->is_big, "not available on the big-board path");
         CU(cudaMemcpyAsync(h->d_rows + (size_t)chain * h->n_pad, d_rows_u16,
                            (size_t)h->cfg.n * sizeof(uint16_t), cudaMemcpyDeviceToDevice,
                            h->stream));

@@ -557,7 +557,8 @@ __global__ void __launch_bounds__(NQ_THREADS, 1)
 
 // Full re-score by the reference's pair test (examples/nqueens/src/lib.rs:74-87), grid over
 // col1; accumulates the number of conflicting pairs into *pairs.
-__global__ void nq_pair_score_kernel(const uint16_t* __restrict__ rows, int n,
+template <typename T>
+__global__ void nq_pair_score_kernel(const T* __restrict__ rows, int n,
                                      unsigned long long* pairs) {
     unsigned long long local = 0;
     for (int col1 = blockIdx.x; col1 < n; col1 += gridDim.x) {

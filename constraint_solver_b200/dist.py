@@ -68,3 +68,22 @@ class BestExchange:
             worst = int(self.eng.scores().argmax())
             self.eng.set_chain_from_device(worst, self.elite.data_ptr())
         return self.best_score, self.best_chain
+
+
+class PartitionedBoard:
+    """ONE very large n-queens instance whose swap neighbourhood is split across ranks
+    (SURVEY 8e, config 5).  Every rank holds a replica (same seed / same rows) and scans a
+    triangular-balanced column slice; per step the 8-byte packed keys are min-all-reduced and
+    every replica applies the same move, so no state ever crosses NVLink."""
+
+    def __init__(self, eng, dist, rank: int, world: int):
+        self.eng, self.dist, self.rank, self.world = eng, dist, rank, world
+        eng.set_partition(rank, world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.key = device_view(eng.part_key_device_ptr(), (1,), "<i8", dev)
+
+    def step(self):
+        self.eng.part_scan()                       # enumerate + delta-score this slice
+        if self.world > 1:
+            self.dist.all_reduce(self.key, op=self.dist.ReduceOp.MIN)  # in place, on device
+        return self.eng.part_apply()               # every replica accepts the winner

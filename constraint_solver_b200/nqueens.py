@@ -89,7 +89,8 @@ class NQueensChains:
     """
 
     def __init__(self, n: int, n_chains: int = 1, *, seed: int = 42, chain_offset: int = 0,
-                 neighbourhood: int = SWAP, trace_capacity: int = 0, device: int = -1):
+                 neighbourhood: int = SWAP, trace_capacity: int = 0, device: int = -1,
+                 force_global: bool = False):
         self._lib = L.load()
         self.n, self.n_chains = int(n), int(n_chains)
         self.neighbourhood = neighbourhood
@@ -97,7 +98,8 @@ class NQueensChains:
         self.chain_offset = chain_offset
         cfg = L.CsNqConfig(n=n, n_chains=n_chains, chain_offset=chain_offset,
                            trace_capacity=trace_capacity, seed=seed, device=device,
-                           neighbourhood=neighbourhood)
+                           neighbourhood=neighbourhood,
+                           flags=L.CS_NQ_FLAG_GLOBAL if force_global else 0)
         h = C.c_void_p()
         rc = self._lib.cs_nq_create(C.byref(cfg), C.byref(h))
         if rc != L.CS_OK:
@@ -249,6 +251,23 @@ class NQueensChains:
         sc, ch = C.c_int64(), C.c_uint32()
         self._check(self._lib.cs_nq_best(self._h, _ptr(rows), C.byref(sc), C.byref(ch)), "cs_nq_best")
         return rows, int(sc.value), int(ch.value)
+
+    # -- one big instance, neighbourhood partitioned across handles / GPUs
+    def set_partition(self, part: int, parts: int):
+        self._check(self._lib.cs_nq_set_partition(self._h, part, parts), "cs_nq_set_partition")
+
+    def part_scan(self):
+        self._check(self._lib.cs_nq_part_scan(self._h), "cs_nq_part_scan")
+
+    def part_key_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.cs_nq_part_key_device_ptr(self._h, C.byref(p)), "cs_nq_part_key_device_ptr")
+        return int(p.value)
+
+    def part_apply(self) -> StepStats:
+        s = L.CsStepStats()
+        self._check(self._lib.cs_nq_part_apply(self._h, C.byref(s)), "cs_nq_part_apply")
+        return self._stats(s)
 
     def best_key_device_ptr(self) -> int:
         p = C.c_void_p()

@@ -38,11 +38,15 @@ extern "C" {
 #define CS_ERR_STATE (-5)
 #define CS_ERR_UNSUPPORTED (-6)
 
-#define CS_ABI_VERSION 1
+#define CS_ABI_VERSION 2
 
 /* Largest board the shared-memory-resident chain kernels take (one CTA holds rows,
  * per-column line sums and both diagonal counter arrays in <= 227 KB). */
 #define CS_NQ_MAX_N_SMEM 16384u
+/* Largest board at all: bigger boards (and CS_NQ_FLAG_GLOBAL) use the L2-resident kernels,
+ * one instance per handle, swap neighbourhood, optionally partitioned across handles/GPUs. */
+#define CS_NQ_MAX_N 1000000u
+#define CS_NQ_FLAG_GLOBAL 1u /* force the global-memory (big board) path for any n */
 
 /* neighbourhood kinds */
 #define CS_NQ_SWAP 0u   /* exchange rows of columns i<j (new; defined against lib.rs:74-87) */
@@ -91,13 +95,14 @@ const char* cs_status_string(int32_t status);
 typedef struct cs_nq_handle cs_nq_handle;
 
 typedef struct cs_nq_config {
-    uint32_t n;              /* board size, 1..CS_NQ_MAX_N_SMEM */
+    uint32_t n;              /* board size, 1..CS_NQ_MAX_N */
     uint32_t n_chains;       /* independent restart chains held by this handle */
     uint32_t chain_offset;   /* global id of local chain 0 (Philox stream id; rank sharding) */
     uint32_t trace_capacity; /* chosen-move log entries kept per chain (0 = no trace) */
     uint64_t seed;           /* Philox key */
     int32_t device;          /* CUDA ordinal; -1 = current device */
     uint32_t neighbourhood;  /* CS_NQ_SWAP or CS_NQ_CHANGE */
+    uint32_t flags;          /* CS_NQ_FLAG_* */
 } cs_nq_config;
 
 /* LocalSearch::new, local-search/src/local_search.rs:277-299 (the handle owns what the
@@ -176,6 +181,20 @@ int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain, const void* 
 /* Device pointer to chain's rows (uint16 [n], padded stride available via *stride_elems). */
 int32_t cs_nq_chain_device_ptr(cs_nq_handle* h, uint32_t chain, void** dptr,
                                uint32_t* stride_elems);
+
+/* --- one very large instance with its neighbourhood split across handles / GPUs (big-board
+ * path only).  Every handle holds a full replica of the same instance; partition `part` of
+ * `parts` scans the columns i of a triangular-balanced slice.  Per step: cs_nq_part_scan on
+ * every handle, min-reduce the 8-byte keys (NCCL all-reduce over the device pointers), then
+ * cs_nq_part_apply on every handle -- all replicas accept the same move, no state moves. */
+int32_t cs_nq_set_partition(cs_nq_handle* h, uint32_t part, uint32_t parts);
+/* enumerate + delta-score this partition's slice; leaves the packed key
+ * ((delta/2 + 2^22) << 40 | i << 20 | j, int64; INT64_MAX = empty) on the device */
+int32_t cs_nq_part_scan(cs_nq_handle* h);
+int32_t cs_nq_part_key_device_ptr(cs_nq_handle* h, void** dptr);
+/* accept the move currently in the key (after the caller's reduce); stats->moves_scored is
+ * what THIS partition scanned */
+int32_t cs_nq_part_apply(cs_nq_handle* h, cs_step_stats* stats);
 
 /* ------------------------------------------------------------------ employee scheduling */
 /* One employee per calendar day (examples/employee-scheduling/src/lib.rs:127-146).  A solution

@@ -35,7 +35,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_abi_version_and_status_strings():
     lib = cs.load()
-    assert lib.cs_abi_version() == 1
+    assert lib.cs_abi_version() == 2
     assert b"no CPU fallback" in lib.cs_status_string(L.CS_ERR_NO_DEVICE)
 
 
@@ -49,10 +49,10 @@ def test_host_philox_mirror_matches_oracle():
 def test_invalid_config_rejected_before_touching_a_device():
     lib = cs.load()
     h = C.c_void_p()
-    bad = L.CsNqConfig(n=0, n_chains=1, chain_offset=0, trace_capacity=0, seed=1, device=-1, neighbourhood=0)
+    bad = L.CsNqConfig(n=0, n_chains=1, chain_offset=0, trace_capacity=0, seed=1, device=-1, neighbourhood=0, flags=0)
     assert lib.cs_nq_create(C.byref(bad), C.byref(h)) == L.CS_ERR_INVALID_ARG
-    big = L.CsNqConfig(n=L.CS_NQ_MAX_N_SMEM + 1, n_chains=1, chain_offset=0, trace_capacity=0, seed=1,
-                       device=-1, neighbourhood=0)
+    big = L.CsNqConfig(n=L.CS_NQ_MAX_N + 1, n_chains=1, chain_offset=0, trace_capacity=0, seed=1,
+                       device=-1, neighbourhood=0, flags=0)
     assert lib.cs_nq_create(C.byref(big), C.byref(h)) == L.CS_ERR_UNSUPPORTED
     assert lib.cs_nq_create(None, C.byref(h)) == L.CS_ERR_INVALID_ARG
     assert lib.cs_nq_destroy(None) == L.CS_ERR_INVALID_ARG

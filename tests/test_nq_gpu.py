@@ -184,7 +184,7 @@ def test_edge_cases_and_errors():
     lib = cs.load()
     import ctypes as C
     h = C.c_void_p()
-    cfg = L.CsNqConfig(n=8, n_chains=1, chain_offset=0, trace_capacity=0, seed=1, device=999, neighbourhood=0)
+    cfg = L.CsNqConfig(n=8, n_chains=1, chain_offset=0, trace_capacity=0, seed=1, device=999, neighbourhood=0, flags=0)
     assert lib.cs_nq_create(C.byref(cfg), C.byref(h)) == L.CS_ERR_INVALID_ARG
 
 
