@@ -153,6 +153,7 @@ def test_million_queens_partition_properties():
         s0 = int(e.scores()[0])
         e.set_partition(63, 64)
         e.part_scan()
+        torch.cuda.synchronize()  # the handle runs on its own stream
         key = int(device_view(e.part_key_device_ptr(), (1,), "<i8", torch.device("cuda", 0)).item())
         v, i, j = (key >> 40) - (1 << 22), (key >> 20) & 0xFFFFF, key & 0xFFFFF
         assert 0 <= i < j < n
