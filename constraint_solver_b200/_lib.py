@@ -98,6 +98,19 @@ class CsEsStepStats(C.Structure):
     ]
 
 
+class CsIlsStats(C.Structure):
+    _fields_ = [
+        ("moves_scored", C.c_uint64),
+        ("ls_steps", C.c_uint64),
+        ("best_key", C.c_int64),
+        ("best_chain", C.c_uint32),
+        ("chains_done", C.c_uint32),
+        ("rounds_run", C.c_uint32),
+        ("device_ms", C.c_float),
+        ("kernel_launches", C.c_uint32),
+    ]
+
+
 CS_ES_CHANGE, CS_ES_SWAP = 0, 1
 CS_ES_MAX_DAYS = 64
 
@@ -136,6 +149,14 @@ SIGNATURES = {
     "cs_nq_part_scan": (C.c_int32, [_VP]),
     "cs_nq_part_key_device_ptr": (C.c_int32, [_VP, _P(_VP)]),
     "cs_nq_part_apply": (C.c_int32, [_VP, _P(CsStepStats)]),
+    "cs_nq_ils_init": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "cs_nq_ils_run": (C.c_int32, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P(CsIlsStats)]),
+    "cs_nq_ils_get_best": (C.c_int32, [_VP, C.c_uint32, _VP, _P(C.c_int64)]),
+    "cs_nq_ils_get_log": (C.c_int32, [_VP, C.c_uint32, _VP, _VP, C.c_uint64, _P(C.c_uint64)]),
+    "cs_es_ils_init": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "cs_es_ils_run": (C.c_int32, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P(CsIlsStats)]),
+    "cs_es_ils_get_best": (C.c_int32, [_VP, C.c_uint32, _VP, _P(C.c_int64), _P(C.c_int64)]),
+    "cs_es_ils_get_log": (C.c_int32, [_VP, C.c_uint32, _VP, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_es_create": (C.c_int32, [_P(CsEsConfig), _VP, _VP, _VP, C.c_uint64, _P(_VP)]),
     "cs_es_destroy": (C.c_int32, [_VP]),
     "cs_es_last_error": (C.c_char_p, [_VP]),

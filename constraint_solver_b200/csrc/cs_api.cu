@@ -11,6 +11,7 @@
 #include "../../include/cs_b200.h"
 #include "nq_kernels.cuh"
 #include "nq_big.cuh"
+#include "ils_kernels.cuh"
 #include "philox.cuh"
 
 using namespace csb;
@@ -75,6 +76,8 @@ int32_t guarded(H* h, F&& f) {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
+
+#include "ils_api.cuh"
 
 // ------------------------------------------------------------------ library-wide
 extern "C" int32_t cs_abi_version(void) { return CS_ABI_VERSION; }
@@ -141,6 +144,7 @@ struct cs_nq_handle {
     unsigned long long* h_scored = nullptr;  // pinned
     uint32_t part = 0, parts = 1;
     unsigned long long ls_no_improve = 0;
+    IlsHost ils;
     std::string err;
 };
 
@@ -172,6 +176,7 @@ NqParams nq_params(cs_nq_handle* h, int first, int count) {
 void nq_free(cs_nq_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->ils.release();
     cudaFree(h->d_rows);
     cudaFree(h->d_best_rows);
     cudaFree(h->d_st);
@@ -768,6 +773,156 @@ extern "C" int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain,
         nq_rescore(h, (int)chain, 1);
         nq_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ------------------------------------------------------------------ n-queens ILS shell
+namespace {
+
+__global__ void nq_gather_keys_kernel(const NqChainState* st, long long* best_key, long long* cur_key,
+                                      int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (best_key) best_key[k] = st[k].best_score;
+    if (cur_key) cur_key[k] = st[k].score;
+}
+
+IlsParams nq_ils_params(cs_nq_handle* h) {
+    IlsParams p = h->ils.params(h->d_rows, h->d_best_rows, h->cfg.seed, h->cfg.chain_offset);
+    p.value_range = (int)h->cfg.n;
+    p.restart_is_perm = 1;
+    p.do_nothing_first = 0;  // nqueens lib.rs:277-280: ChangeSubset listed first
+    p.k_before_shuffle = 0;  // lib.rs:303-306: shuffle, then the subset size
+    return p;
+}
+
+}  // namespace
+
+extern "C" int32_t cs_nq_ils_init(cs_nq_handle* h, uint32_t cap, uint32_t log_cap) {
+    return guarded(h, [&] {
+        REQUIRE(!h->is_big, "the ILS shell runs on the shared-memory chain path");
+        REQUIRE(cap >= 1 && cap <= ILS_MAX_CAP, "best_solutions_capacity must be 1..64");
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        const int nc = (int)h->cfg.n_chains;
+        h->ils.alloc(nc, (int)h->cfg.n, h->n_pad, (int)cap, (int)log_cap);
+        ils_reset_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->ils.d_st, h->ils.d_cur_key,
+                                                                    h->ils.d_skip, nc);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h->ils.d_cur, h->d_rows, (size_t)nc * h->n_pad * sizeof(uint16_t),
+                           cudaMemcpyDeviceToDevice, h->stream));
+        nq_gather_keys_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_st, nullptr,
+                                                                         h->ils.d_cur_key, nc);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    });
+}
+
+extern "C" int32_t cs_nq_ils_run(cs_nq_handle* h, uint32_t rounds, uint64_t ls_max_iterations,
+                                 uint64_t allow, uint32_t stop_when_any_best, cs_ils_stats* stats) {
+    return guarded(h, [&] {
+        if (!h->ils.ready) throw StateFail{"call cs_nq_ils_init first"};
+        const int nc = (int)h->cfg.n_chains;
+        IlsParams ip = nq_ils_params(h);
+        NqParams lp = nq_params(h, 0, nc);
+        lp.max_steps = ls_max_iterations;
+        lp.allow_no_improve = allow;
+        lp.ls_mode = 1;
+        lp.skip = h->ils.d_skip;
+        const int ls_grid = nc < h->sm_count ? nc : h->sm_count;
+        const int ig = ils_grid(nc, h->sm_count);
+        unsigned launches = 0, run = 0;
+        CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
+        CU(cudaEventRecord(h->ev0, h->stream));
+        for (uint32_t r = 0; r < rounds; ++r) {
+            ils_perturb_kernel<<<ig, ILS_THREADS, h->ils.perturb_smem, h->stream>>>(ip);
+            CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+            nq_step_kernel<NQ_TI><<<ls_grid, h->threads, h->smem, h->stream>>>(lp);
+            nq_gather_keys_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_st, h->ils.d_neu_key,
+                                                                             nullptr, nc);
+            ils_accept_kernel<<<ig, ILS_THREADS, 0, h->stream>>>(ip);
+            CU(cudaGetLastError());
+            launches += 4;
+            ++run;
+            if (stop_when_any_best) {
+                ils_summary_kernel<<<1, 1024, 0, h->stream>>>(ip, h->ils.d_sum);
+                CU(cudaMemcpyAsync(h->ils.h_sum, h->ils.d_sum, sizeof(IlsSummary),
+                                   cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                ++launches;
+                if (h->ils.h_sum->chains_done) break;
+            }
+        }
+        ils_summary_kernel<<<1, 1024, 0, h->stream>>>(ip, h->ils.d_sum);
+        CU(cudaMemcpyAsync(h->ils.h_sum, h->ils.d_sum, sizeof(IlsSummary), cudaMemcpyDeviceToHost,
+                           h->stream));
+        // publish the ILS current as the chains' solution so the ordinary getters see it
+        CU(cudaMemcpyAsync(h->d_rows, h->ils.d_cur, (size_t)nc * h->n_pad * sizeof(uint16_t),
+                           cudaMemcpyDeviceToDevice, h->stream));
+        nq_rescore(h, 0, nc);
+        nq_refresh_stats(h);
+        CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (stats) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            stats->moves_scored = h->h_totals[0];
+            stats->ls_steps = h->h_totals[1];
+            stats->best_key = h->ils.h_sum->best_key;
+            stats->best_chain = h->ils.h_sum->best_chain;
+            stats->chains_done = h->ils.h_sum->chains_done;
+            stats->rounds_run = run;
+            stats->device_ms = ms;
+            stats->kernel_launches = launches + 3;
+        }
+    });
+}
+
+extern "C" int32_t cs_nq_ils_get_best(cs_nq_handle* h, uint32_t chain, int64_t* rows, int64_t* score) {
+    return guarded(h, [&] {
+        if (!h->ils.ready) throw StateFail{"call cs_nq_ils_init first"};
+        nq_check_range(h, chain, 1);
+        IlsChainState st;
+        CU(cudaMemcpyAsync(&st, h->ils.d_st + chain, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+        unsigned char slot = 0;
+        CU(cudaMemcpyAsync(&slot, h->ils.d_order + (size_t)chain * h->ils.cap, 1, cudaMemcpyDeviceToHost,
+                           h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (!st.size) throw StateFail{"no round has run yet (the reference unwrap()s None here)"};
+        if (score) {
+            CU(cudaMemcpyAsync(score, h->ils.d_bset_key + (size_t)chain * h->ils.cap + slot,
+                               sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+        if (rows)
+            nq_download(h, h->ils.d_bset + ((size_t)chain * h->ils.cap + slot) * h->n_pad -
+                               (size_t)0 * h->n_pad, 0, 1, rows);
+    });
+}
+
+extern "C" int32_t cs_nq_ils_get_log(cs_nq_handle* h, uint32_t chain, int64_t* new_key,
+                                     uint32_t* choice, uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        if (!h->ils.ready) throw StateFail{"call cs_nq_ils_init first"};
+        nq_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        IlsChainState st;
+        CU(cudaMemcpyAsync(&st, h->ils.d_st + chain, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        *n_out = st.log_len;
+        uint64_t k = st.log_len;
+        if (k > (uint64_t)h->ils.log_cap) k = h->ils.log_cap;
+        if (k > cap) k = cap;
+        if (!k) return;
+        std::vector<IlsLogEntry> log(k);
+        CU(cudaMemcpyAsync(log.data(), h->ils.d_log + (size_t)chain * h->ils.log_cap,
+                           k * sizeof(IlsLogEntry), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint64_t q = 0; q < k; ++q) {
+            if (new_key) new_key[q] = log[q].new_key;
+            if (choice) choice[q] = log[q].choice;
+        }
     });
 }
 

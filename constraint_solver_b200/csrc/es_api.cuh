@@ -29,6 +29,7 @@ struct cs_es_handle {
     size_t stage_chains = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;
+    IlsHost ils;
     std::string err;
 };
 
@@ -54,6 +55,7 @@ EsParams es_params(cs_es_handle* h, int first, int count) {
 void es_free(cs_es_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->ils.release();
     cudaFree(h->d_a);
     cudaFree(h->d_best_a);
     cudaFree(h->d_hol);
@@ -571,5 +573,147 @@ extern "C" int32_t cs_es_chain_device_ptr(cs_es_handle* h, uint32_t chain, void*
         REQUIRE(dptr, "dptr is NULL");
         *dptr = (void*)(h->d_a + (size_t)chain * h->stride);
         if (n_slots) *n_slots = (uint32_t)h->stride;
+    });
+}
+
+// ------------------------------------------------------------------ scheduling ILS shell
+namespace {
+
+__global__ void es_gather_keys_kernel(const EsChainState* st, long long* best_key, long long* cur_key,
+                                      int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (best_key) best_key[k] = (st[k].best_hard << 32) | st[k].best_soft;
+    if (cur_key) cur_key[k] = (st[k].hard << 32) | st[k].soft;
+}
+
+IlsParams es_ils_params(cs_es_handle* h) {
+    IlsParams p = h->ils.params(h->d_a, h->d_best_a, h->cfg.seed, h->cfg.chain_offset);
+    p.value_range = h->K.E;
+    p.restart_is_perm = 0;
+    p.do_nothing_first = 1;  // employee-scheduling lib.rs:574-577: DoNothing listed first
+    p.k_before_shuffle = 1;  // lib.rs:600-605: subset size, then the shuffle
+    return p;
+}
+
+}  // namespace
+
+extern "C" int32_t cs_es_ils_init(cs_es_handle* h, uint32_t cap, uint32_t log_cap) {
+    return guarded(h, [&] {
+        REQUIRE(cap >= 1 && cap <= ILS_MAX_CAP, "best_solutions_capacity must be 1..64");
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        const int nc = (int)h->cfg.n_chains;
+        h->ils.alloc(nc, h->stride, h->stride, (int)cap, (int)log_cap);
+        ils_reset_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->ils.d_st, h->ils.d_cur_key,
+                                                                    h->ils.d_skip, nc);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h->ils.d_cur, h->d_a, (size_t)nc * h->stride * sizeof(uint16_t),
+                           cudaMemcpyDeviceToDevice, h->stream));
+        es_gather_keys_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_st, nullptr, h->ils.d_cur_key, nc);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    });
+}
+
+extern "C" int32_t cs_es_ils_run(cs_es_handle* h, uint32_t rounds, uint64_t ls_max_iterations,
+                                 uint64_t allow, uint32_t stop_when_any_best, cs_ils_stats* stats) {
+    return guarded(h, [&] {
+        if (!h->ils.ready) throw StateFail{"call cs_es_ils_init first"};
+        const int nc = (int)h->cfg.n_chains;
+        IlsParams ip = es_ils_params(h);
+        EsParams lp = es_params(h, 0, nc);
+        lp.max_steps = ls_max_iterations;
+        lp.allow_no_improve = allow;
+        lp.ls_mode = 1;
+        lp.skip = h->ils.d_skip;
+        const int ls_grid = nc < h->grid_cap ? nc : h->grid_cap;
+        const int ig = nc < 4096 ? nc : 4096;
+        unsigned launches = 0, run = 0;
+        CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
+        CU(cudaEventRecord(h->ev0, h->stream));
+        for (uint32_t r = 0; r < rounds; ++r) {
+            ils_perturb_kernel<<<ig, ILS_THREADS, h->ils.perturb_smem, h->stream>>>(ip);
+            CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+            es_step_kernel<<<ls_grid, h->threads, h->smem, h->stream>>>(lp);
+            es_gather_keys_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_st, h->ils.d_neu_key, nullptr, nc);
+            ils_accept_kernel<<<ig, ILS_THREADS, 0, h->stream>>>(ip);
+            CU(cudaGetLastError());
+            launches += 4;
+            ++run;
+            if (stop_when_any_best) {
+                ils_summary_kernel<<<1, 1024, 0, h->stream>>>(ip, h->ils.d_sum);
+                CU(cudaMemcpyAsync(h->ils.h_sum, h->ils.d_sum, sizeof(IlsSummary), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                ++launches;
+                if (h->ils.h_sum->chains_done) break;
+            }
+        }
+        ils_summary_kernel<<<1, 1024, 0, h->stream>>>(ip, h->ils.d_sum);
+        CU(cudaMemcpyAsync(h->ils.h_sum, h->ils.d_sum, sizeof(IlsSummary), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->d_a, h->ils.d_cur, (size_t)nc * h->stride * sizeof(uint16_t),
+                           cudaMemcpyDeviceToDevice, h->stream));
+        es_rescore(h, 0, nc);
+        es_refresh_stats(h);
+        CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (stats) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            stats->moves_scored = h->h_totals[0];
+            stats->ls_steps = h->h_totals[1];
+            stats->best_key = h->ils.h_sum->best_key;
+            stats->best_chain = h->ils.h_sum->best_chain;
+            stats->chains_done = h->ils.h_sum->chains_done;
+            stats->rounds_run = run;
+            stats->device_ms = ms;
+            stats->kernel_launches = launches + 3;
+        }
+    });
+}
+
+extern "C" int32_t cs_es_ils_get_best(cs_es_handle* h, uint32_t chain, int64_t* rows, int64_t* hard,
+                                      int64_t* soft) {
+    return guarded(h, [&] {
+        if (!h->ils.ready) throw StateFail{"call cs_es_ils_init first"};
+        es_check_range(h, chain, 1);
+        IlsChainState st;
+        CU(cudaMemcpyAsync(&st, h->ils.d_st + chain, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+        unsigned char slot = 0;
+        CU(cudaMemcpyAsync(&slot, h->ils.d_order + (size_t)chain * h->ils.cap, 1, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (!st.size) throw StateFail{"no round has run yet (the reference unwrap()s None here)"};
+        long long key = 0;
+        CU(cudaMemcpyAsync(&key, h->ils.d_bset_key + (size_t)chain * h->ils.cap + slot, sizeof key,
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (hard) *hard = key >> 32;
+        if (soft) *soft = key & 0xffffffffll;
+        if (rows) es_download(h, h->ils.d_bset + ((size_t)chain * h->ils.cap + slot) * h->stride, 0, 1, rows);
+    });
+}
+
+extern "C" int32_t cs_es_ils_get_log(cs_es_handle* h, uint32_t chain, int64_t* new_key, uint32_t* choice,
+                                     uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        if (!h->ils.ready) throw StateFail{"call cs_es_ils_init first"};
+        es_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        IlsChainState st;
+        CU(cudaMemcpyAsync(&st, h->ils.d_st + chain, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        *n_out = st.log_len;
+        uint64_t k = st.log_len;
+        if (k > (uint64_t)h->ils.log_cap) k = h->ils.log_cap;
+        if (k > cap) k = cap;
+        if (!k) return;
+        std::vector<IlsLogEntry> log(k);
+        CU(cudaMemcpyAsync(log.data(), h->ils.d_log + (size_t)chain * h->ils.log_cap, k * sizeof(IlsLogEntry),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint64_t q = 0; q < k; ++q) {
+            if (new_key) new_key[q] = log[q].new_key;
+            if (choice) choice[q] = log[q].choice;
+        }
     });
 }

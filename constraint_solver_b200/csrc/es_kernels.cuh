@@ -64,6 +64,7 @@ struct EsParams {
     int ls_mode;
     long long* dump_h;  // debug: every candidate's (dhard, dsoft)
     long long* dump_s;
+    const unsigned int* skip;  // optional [chains]: 1 = leave the chain alone (ILS)
 };
 
 // per-chain shared state
@@ -438,6 +439,7 @@ __global__ void es_step_kernel(EsParams p) {
         const int local = s.misc[ES_BCAST];
         if (local >= p.n_chains) break;
         const int chain = p.first_chain + local;
+        if (p.skip && p.skip[chain]) continue;
         uint16_t* ga = p.a + (size_t)chain * p.stride;
         EsChainState* st = p.st + chain;
         __syncthreads();

@@ -56,6 +56,7 @@ struct NqParams {
     int ls_mode;                          // 1: LocalSearch::execute bookkeeping
     int kind;                             // 0 swap, 1 change
     long long* dump;                      // debug: every candidate delta (one chain)
+    const unsigned int* skip;             // optional [chains]: 1 = leave the chain alone (ILS)
 };
 
 // ------------------------------------------------------------------ shared memory view
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
         const int local = s.red[96];
         if (local >= p.n_chains) break;
         const int chain = p.first_chain + local;
+        if (p.skip && p.skip[chain]) continue;
         uint16_t* grow = p.rows + (size_t)chain * p.n_pad;
         NqChainState* st = p.st + chain;
 

@@ -252,6 +252,39 @@ class NQueensChains:
         self._check(self._lib.cs_nq_best(self._h, _ptr(rows), C.byref(sc), C.byref(ch)), "cs_nq_best")
         return rows, int(sc.value), int(ch.value)
 
+
+    # -- iterated local search shell (iterated_local_search.rs:96-203)
+    def ils_init(self, best_solutions_capacity: int = 32, log_capacity: int = 0):
+        self._ils_log_cap = log_capacity
+        self._check(self._lib.cs_nq_ils_init(self._h, best_solutions_capacity, log_capacity),
+                    "cs_nq_ils_init")
+
+    def ils_run(self, rounds: int, ls_max_iterations: int, allow_no_improvement_for: int,
+                stop_when_any_best: bool = False):
+        s = L.CsIlsStats()
+        self._check(self._lib.cs_nq_ils_run(self._h, rounds, ls_max_iterations, allow_no_improvement_for,
+                                            1 if stop_when_any_best else 0, C.byref(s)), "cs_nq_ils_run")
+        return dict(moves_scored=int(s.moves_scored), ls_steps=int(s.ls_steps), best_key=int(s.best_key),
+                    best_chain=int(s.best_chain), chains_done=int(s.chains_done),
+                    rounds_run=int(s.rounds_run), device_ms=float(s.device_ms),
+                    kernel_launches=int(s.kernel_launches))
+
+    def ils_log(self, chain: int = 0):
+        n = C.c_uint64()
+        cap = max(getattr(self, "_ils_log_cap", 0), 1)
+        key = np.empty(cap, dtype=np.int64)
+        choice = np.empty(cap, dtype=np.uint32)
+        self._check(self._lib.cs_nq_ils_get_log(self._h, chain, _ptr(key), _ptr(choice), cap, C.byref(n)),
+                    "cs_nq_ils_get_log")
+        k = min(int(n.value), getattr(self, "_ils_log_cap", 0))
+        return key[:k], choice[:k], int(n.value)
+
+    def ils_best(self, chain: int = 0):
+        rows = np.empty(self.n, dtype=np.int64)
+        sc = C.c_int64()
+        self._check(self._lib.cs_nq_ils_get_best(self._h, chain, _ptr(rows), C.byref(sc)), "cs_nq_ils_get_best")
+        return rows, int(sc.value)
+
     # -- one big instance, neighbourhood partitioned across handles / GPUs
     def set_partition(self, part: int, parts: int):
         self._check(self._lib.cs_nq_set_partition(self._h, part, parts), "cs_nq_set_partition")

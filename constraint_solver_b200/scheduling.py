@@ -237,6 +237,40 @@ class ScheduleChains:
         self._check(self._lib.cs_es_best(self._h, _ptr(rows), C.byref(h), C.byref(s), C.byref(c)), "cs_es_best")
         return rows, int(h.value), int(s.value), int(c.value)
 
+
+    # -- iterated local search shell (iterated_local_search.rs:96-203)
+    def ils_init(self, best_solutions_capacity: int = 32, log_capacity: int = 0):
+        self._ils_log_cap = log_capacity
+        self._check(self._lib.cs_es_ils_init(self._h, best_solutions_capacity, log_capacity),
+                    "cs_es_ils_init")
+
+    def ils_run(self, rounds: int, ls_max_iterations: int, allow_no_improvement_for: int,
+                stop_when_any_best: bool = False):
+        s = L.CsIlsStats()
+        self._check(self._lib.cs_es_ils_run(self._h, rounds, ls_max_iterations, allow_no_improvement_for,
+                                            1 if stop_when_any_best else 0, C.byref(s)), "cs_es_ils_run")
+        return dict(moves_scored=int(s.moves_scored), ls_steps=int(s.ls_steps), best_key=int(s.best_key),
+                    best_chain=int(s.best_chain), chains_done=int(s.chains_done),
+                    rounds_run=int(s.rounds_run), device_ms=float(s.device_ms),
+                    kernel_launches=int(s.kernel_launches))
+
+    def ils_log(self, chain: int = 0):
+        n = C.c_uint64()
+        cap = max(getattr(self, "_ils_log_cap", 0), 1)
+        key = np.empty(cap, dtype=np.int64)
+        choice = np.empty(cap, dtype=np.uint32)
+        self._check(self._lib.cs_es_ils_get_log(self._h, chain, _ptr(key), _ptr(choice), cap, C.byref(n)),
+                    "cs_es_ils_get_log")
+        k = min(int(n.value), getattr(self, "_ils_log_cap", 0))
+        return key[:k], choice[:k], int(n.value)
+
+    def ils_best(self, chain: int = 0):
+        rows = np.empty(self.n_slots, dtype=np.int64)
+        h, s = C.c_int64(), C.c_int64()
+        self._check(self._lib.cs_es_ils_get_best(self._h, chain, _ptr(rows), C.byref(h), C.byref(s)),
+                    "cs_es_ils_get_best")
+        return rows, int(h.value), int(s.value)
+
     def best_key_device_ptr(self) -> int:
         p = C.c_void_p()
         self._check(self._lib.cs_es_best_key_device_ptr(self._h, C.byref(p)), "cs_es_best_key_device_ptr")

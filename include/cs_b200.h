@@ -196,6 +196,41 @@ int32_t cs_nq_part_key_device_ptr(cs_nq_handle* h, void** dptr);
  * what THIS partition scanned */
 int32_t cs_nq_part_apply(cs_nq_handle* h, cs_step_stats* stats);
 
+/* ------------------------------------------------------------------ iterated local search */
+/* IteratedLocalSearch (local-search/src/iterated_local_search.rs:96-203) for every chain of a
+ * handle at once: perturbation (nqueens lib.rs:285-320 / employee-scheduling lib.rs:582-613),
+ * LocalSearch::execute, History::local_search_chose_solution (bounded best-set,
+ * local_search.rs:205-218), AcceptanceCriterion::choose weights 1:5:1 (:51-71), random restart
+ * every 50th round (:185-191).  Random choices come from the chain's Philox stream
+ * (purpose CS_PHILOX_PERTURB) so a chain replays bit-identically on the CPU. */
+typedef struct cs_ils_stats {
+    uint64_t moves_scored;   /* candidates delta-scored by the local searches of this call */
+    uint64_t ls_steps;       /* accepted LS moves */
+    int64_t best_key;        /* best over chains of History::get_best: n-queens score;
+                                scheduling hard << 32 | soft; INT64_MAX before any round */
+    uint32_t best_chain;
+    uint32_t chains_done;    /* chains whose best is_best */
+    uint32_t rounds_run;     /* execute_round calls issued by this call */
+    float device_ms;
+    uint32_t kernel_launches;
+} cs_ils_stats;
+
+/* IteratedLocalSearch::new (:130-156): current := each chain's present solution, empty
+ * history of capacity best_solutions_capacity (1..64); log_capacity rounds of
+ * (new local-minimum key, acceptance choice) are kept per chain for replay checks. */
+int32_t cs_nq_ils_init(cs_nq_handle* h, uint32_t best_solutions_capacity, uint32_t log_capacity);
+/* `rounds` x execute_round (:173-202) with LocalSearch::execute(perturbed,
+ * allow_no_improvement_for) bounded by ls_max_iterations.  stop_when_any_best != 0 checks
+ * after every round and returns as soon as some chain's best is_best. */
+int32_t cs_nq_ils_run(cs_nq_handle* h, uint32_t rounds, uint64_t ls_max_iterations,
+                      uint64_t allow_no_improvement_for, uint32_t stop_when_any_best,
+                      cs_ils_stats* stats);
+/* get_best_solution (:165-167) of one chain; CS_ERR_STATE before the first round (the
+ * reference unwrap()s None there). */
+int32_t cs_nq_ils_get_best(cs_nq_handle* h, uint32_t chain, int64_t* rows, int64_t* score);
+int32_t cs_nq_ils_get_log(cs_nq_handle* h, uint32_t chain, int64_t* new_key, uint32_t* choice,
+                          uint64_t cap, uint64_t* n_out);
+
 /* ------------------------------------------------------------------ employee scheduling */
 /* One employee per calendar day (examples/employee-scheduling/src/lib.rs:127-146).  A solution
  * is the reference's `date_to_employee`: n_days + 1 int64 employee ids -- the generator pushes
@@ -287,6 +322,15 @@ int32_t cs_es_best(cs_es_handle* h, int64_t* rows, int64_t* hard, int64_t* soft,
 /* device int64: (hard << 48) | (soft << 32) | global chain id */
 int32_t cs_es_best_key_device_ptr(cs_es_handle* h, void** dptr);
 int32_t cs_es_chain_device_ptr(cs_es_handle* h, uint32_t chain, void** dptr, uint32_t* n_slots);
+/* ILS shell, see cs_nq_ils_*; the perturbation may rewrite the phantom slot (lib.rs:599-608) */
+int32_t cs_es_ils_init(cs_es_handle* h, uint32_t best_solutions_capacity, uint32_t log_capacity);
+int32_t cs_es_ils_run(cs_es_handle* h, uint32_t rounds, uint64_t ls_max_iterations,
+                      uint64_t allow_no_improvement_for, uint32_t stop_when_any_best,
+                      cs_ils_stats* stats);
+int32_t cs_es_ils_get_best(cs_es_handle* h, uint32_t chain, int64_t* rows, int64_t* hard,
+                           int64_t* soft);
+int32_t cs_es_ils_get_log(cs_es_handle* h, uint32_t chain, int64_t* new_key, uint32_t* choice,
+                          uint64_t cap, uint64_t* n_out);
 
 #ifdef __cplusplus
 }

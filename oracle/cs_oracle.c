@@ -523,3 +523,215 @@ int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
     if (checksum) *checksum = sum;
     return n_moves;
 }
+
+/* ------------------------------------------------------------------ iterated local search */
+/* IteratedLocalSearch::execute_round, local-search/src/iterated_local_search.rs:173-202, with
+ *   - History::local_search_chose_solution (bounded best-set, BTreeSet ordered by
+ *     (score, solution)), local_search.rs:205-218;
+ *   - AcceptanceCriterion::choose weights {existing 1, new 5, random best 1}, :51-71;
+ *   - the plug-in perturbations (nqueens lib.rs:291-319, employee-scheduling lib.rs:588-612);
+ *   - random restart every 50th round, iterated_local_search.rs:185-191.
+ * Random choices are restated over ONE Philox stream per chain (purpose 1), draw t after draw
+ * t-1:  weighted strategy pick = mulhi(u,110); gen_range(1..=m) = 1 + mulhi(u,m);
+ * shuffle = Fisher-Yates k=len-1..1 swap(k, mulhi(u,k+1)); choose = mulhi(u,len);
+ * acceptance = mulhi(u,7).  (rand 0.8.5's own algorithms are un-vendored: parity unpinned.)
+ * A solution is a vector of `len` small integers with an int64 score key (n-queens: the
+ * score; scheduling: hard << 32 | soft) -- lexicographic (key, vector) is the derived Ord. */
+typedef struct {
+    uint64_t seed;
+    uint32_t chain;
+    uint64_t t;
+} orc_rng;
+
+static uint32_t rng_next(orc_rng* r) { return orc_philox_draw(r->seed, r->chain, 1u, r->t++); }
+static int64_t rng_below(orc_rng* r, int64_t m) {
+    return (int64_t)(((uint64_t)rng_next(r) * (uint64_t)m) >> 32);
+}
+
+typedef int64_t (*orc_ls_fn)(void* ctx, int64_t* sol); /* in: start, out: best; returns key */
+typedef void (*orc_restart_fn)(void* ctx, orc_rng* r, int64_t* sol);
+
+static int sol_cmp(int64_t ka, const int64_t* a, int64_t kb, const int64_t* b, int64_t len) {
+    if (ka != kb) return ka < kb ? -1 : 1;
+    for (int64_t i = 0; i < len; ++i)
+        if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    return 0;
+}
+
+static int64_t ils_core(void* ctx, orc_ls_fn ls, orc_restart_fn restart, uint64_t seed,
+                        uint32_t chain, int64_t len, int64_t value_range, int do_nothing_first,
+                        int k_before_shuffle, int best_cap, uint64_t rounds, int64_t* current,
+                        int64_t* best_out, int64_t* best_key_out, int64_t* round_new_key,
+                        int64_t* round_choice) {
+    orc_rng rng = {seed, chain, 0};
+    const size_t bytes = sizeof(int64_t) * (size_t)len;
+    int64_t* set = (int64_t*)malloc(bytes * (size_t)best_cap); /* sorted ascending */
+    int64_t* set_key = (int64_t*)malloc(sizeof(int64_t) * (size_t)best_cap);
+    int64_t* work = (int64_t*)malloc(bytes);
+    int64_t* idx = (int64_t*)malloc(bytes);
+    int size = 0;
+    uint64_t done_rounds = 0;
+    for (uint64_t it = 1; it <= rounds; ++it) {
+        if (size > 0 && set_key[0] == 0) break; /* :175-184 best is_best -> nothing more to do */
+        done_rounds = it;
+        if (it % 50 == 0) restart(ctx, &rng, current); /* :185-191 */
+        memcpy(work, current, bytes);
+        /* perturbation */
+        const int64_t pick = rng_below(&rng, 110);
+        const int change = do_nothing_first ? (pick >= 10) : (pick < 100);
+        if (change) {
+            int in_best = 0; /* history.is_best_solution(current): BTreeSet::contains */
+            for (int e = 0; e < size && !in_best; ++e)
+                in_best = (memcmp(set + (size_t)e * len, current, bytes) == 0);
+            int64_t kmax = in_best ? len / 20 : len / 2;
+            if (kmax < 1) kmax = 1;
+            if (kmax > len) kmax = len;
+            int64_t k = 0;
+            if (k_before_shuffle) k = 1 + rng_below(&rng, kmax);
+            for (int64_t i = 0; i < len; ++i) idx[i] = i;
+            for (int64_t q = len - 1; q >= 1; --q) {
+                const int64_t j = rng_below(&rng, q + 1);
+                const int64_t tmp = idx[q];
+                idx[q] = idx[j];
+                idx[j] = tmp;
+            }
+            if (!k_before_shuffle) k = 1 + rng_below(&rng, kmax);
+            for (int64_t q = 0; q < k; ++q) work[idx[q]] = rng_below(&rng, value_range);
+        }
+        /* local search: work := best found, returns its key (:195-197) */
+        const int64_t nkey = ls(ctx, work);
+        if (round_new_key) round_new_key[it - 1] = nkey;
+        /* history.local_search_chose_solution(new), local_search.rs:205-218 */
+        int do_insert = 0;
+        if (size < best_cap) {
+            do_insert = 1;
+        } else if (nkey <= set_key[size - 1]) {
+            --size; /* remove the worst */
+            do_insert = 1;
+        }
+        if (do_insert) {
+            int pos = 0, dup = 0;
+            for (; pos < size; ++pos) {
+                const int c = sol_cmp(set_key[pos], set + (size_t)pos * len, nkey, work, len);
+                if (c == 0) dup = 1;
+                if (c >= 0) break;
+            }
+            if (!dup) {
+                memmove(set + (size_t)(pos + 1) * len, set + (size_t)pos * len, bytes * (size_t)(size - pos));
+                memmove(set_key + pos + 1, set_key + pos, sizeof(int64_t) * (size_t)(size - pos));
+                memcpy(set + (size_t)pos * len, work, bytes);
+                set_key[pos] = nkey;
+                ++size;
+            }
+        }
+        /* acceptance_criterion.choose, iterated_local_search.rs:51-71 */
+        const int64_t rb = rng_below(&rng, size);
+        const int64_t w = rng_below(&rng, 7);
+        if (round_choice) round_choice[it - 1] = w == 0 ? 0 : (w <= 5 ? 1 : 2);
+        if (w >= 1 && w <= 5) memcpy(current, work, bytes);
+        else if (w == 6) memcpy(current, set + (size_t)rb * len, bytes);
+    }
+    if (size > 0) {
+        memcpy(best_out, set, bytes);
+        *best_key_out = set_key[0];
+    } else {
+        memcpy(best_out, current, bytes);
+        *best_key_out = -1;
+    }
+    free(set);
+    free(set_key);
+    free(work);
+    free(idx);
+    return (int64_t)done_rounds;
+}
+
+typedef struct {
+    int64_t n;
+    int kind;
+    uint64_t allow, iters;
+} nq_ils_ctx;
+
+static int64_t nq_ils_ls(void* c, int64_t* sol) {
+    nq_ils_ctx* x = (nq_ils_ctx*)c;
+    int64_t best = 0;
+    orc_nq_local_search(sol, x->n, x->kind, ORC_TIE_MOVE_ORDER, x->allow, x->iters, 0, &best, NULL,
+                        NULL, NULL, NULL, NULL, 0);
+    return best;
+}
+
+static void nq_ils_restart(void* c, orc_rng* r, int64_t* sol) {
+    nq_ils_ctx* x = (nq_ils_ctx*)c;
+    for (int64_t i = 0; i < x->n; ++i) sol[i] = i;
+    for (int64_t q = x->n - 1; q >= 1; --q) {
+        const int64_t j = rng_below(r, q + 1);
+        const int64_t t = sol[q];
+        sol[q] = sol[j];
+        sol[j] = t;
+    }
+}
+
+/* n-queens ILS chain: initial solution = orc_nq_init_perm(seed, chain) (ILS::new, :141-142).
+ * Returns the rounds run; best_rows/best_score = history.get_best() (:165-167). */
+int64_t orc_nq_ils(uint64_t seed, uint32_t chain, int64_t n, int kind, uint64_t ls_max_iterations,
+                   uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
+                   int64_t* best_rows, int64_t* best_score, int64_t* current_out,
+                   int64_t* round_new_score, int64_t* round_choice) {
+    nq_ils_ctx ctx = {n, kind, allow_no_improvement_for, ls_max_iterations};
+    int64_t* current = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    orc_nq_init_perm(seed, chain, n, current);
+    const int64_t r = ils_core(&ctx, nq_ils_ls, nq_ils_restart, seed, chain, n, n, 0, 0, best_cap,
+                               rounds, current, best_rows, best_score, round_new_score, round_choice);
+    if (current_out) memcpy(current_out, current, sizeof(int64_t) * (size_t)n);
+    free(current);
+    return r;
+}
+
+typedef struct {
+    int64_t D, E;
+    int wd;
+    const int64_t *he, *hd, *emp;
+    int64_t nh;
+    uint64_t allow, iters;
+} es_ils_ctx;
+
+/* the ILS vectors of the scheduling problem hold employee INDICES (0..E-1) over D+1 slots */
+static int64_t es_ils_ls(void* c, int64_t* sol) {
+    es_ils_ctx* x = (es_ils_ctx*)c;
+    int64_t* a = (int64_t*)malloc(sizeof(int64_t) * (size_t)x->D);
+    for (int64_t i = 0; i < x->D; ++i) a[i] = x->emp[sol[i]];
+    int64_t bh = 0, bs = 0;
+    orc_es_local_search(a, x->D, x->wd, x->he, x->hd, x->nh, x->emp, x->E, x->allow, x->iters, &bh,
+                        &bs, NULL, NULL, NULL, NULL, NULL, NULL, 0);
+    for (int64_t i = 0; i < x->D; ++i) {
+        int64_t e = 0;
+        while (x->emp[e] != a[i]) ++e;
+        sol[i] = e; /* phantom slot sol[D] is untouched by the local search */
+    }
+    free(a);
+    return (bh << 32) | bs;
+}
+
+static void es_ils_restart(void* c, orc_rng* r, int64_t* sol) {
+    es_ils_ctx* x = (es_ils_ctx*)c;
+    for (int64_t s = 0; s <= x->D; ++s) sol[s] = rng_below(r, x->E);
+}
+
+int64_t orc_es_ils(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
+                   const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                   const int64_t* employees, int64_t E, uint64_t ls_max_iterations,
+                   uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
+                   int64_t* best_idx /*[D+1] employee indices*/, int64_t* best_hard,
+                   int64_t* best_soft, int64_t* round_new_key, int64_t* round_choice) {
+    es_ils_ctx ctx = {D, E, start_weekday, hol_emp, hol_day, employees, n_hol,
+                      allow_no_improvement_for, ls_max_iterations};
+    int64_t* current = (int64_t*)malloc(sizeof(int64_t) * (size_t)(D + 1));
+    for (int64_t s = 0; s <= D; ++s) /* same draws as orc_es_init, as indices */
+        current[s] = (int64_t)(((uint64_t)orc_philox_draw(seed, chain, 0u, (uint64_t)s) * (uint64_t)E) >> 32);
+    int64_t key = 0;
+    const int64_t r = ils_core(&ctx, es_ils_ls, es_ils_restart, seed, chain, D + 1, E, 1, 1, best_cap,
+                               rounds, current, best_idx, &key, round_new_key, round_choice);
+    *best_hard = key < 0 ? -1 : key >> 32;
+    *best_soft = key < 0 ? -1 : key & 0xffffffffll;
+    free(current);
+    return r;
+}

@@ -127,6 +127,18 @@ int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
                                const int64_t* y, int64_t n_moves, int threads,
                                int64_t* checksum);
 
+/* ---- iterated local search (iterated_local_search.rs:173-202; see cs_oracle.c) ---- */
+int64_t orc_nq_ils(uint64_t seed, uint32_t chain, int64_t n, int kind, uint64_t ls_max_iterations,
+                   uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
+                   int64_t* best_rows, int64_t* best_score, int64_t* current_out,
+                   int64_t* round_new_score, int64_t* round_choice);
+int64_t orc_es_ils(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
+                   const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                   const int64_t* employees, int64_t E, uint64_t ls_max_iterations,
+                   uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
+                   int64_t* best_idx, int64_t* best_hard, int64_t* best_soft,
+                   int64_t* round_new_key, int64_t* round_choice);
+
 #ifdef __cplusplus
 }
 #endif

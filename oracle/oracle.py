@@ -45,6 +45,8 @@ def lib():
         _lib.orc_es_baseline_sample.restype = I64
         _lib.orc_days_from_civil.restype = I64
         _lib.orc_philox_draw.restype = C.c_uint32
+        _lib.orc_nq_ils.restype = I64
+        _lib.orc_es_ils.restype = I64
     return _lib
 
 
@@ -229,3 +231,37 @@ def es_baseline_sample(a, employees, x, y, kind, threads, start_weekday=0, holid
                                      C.c_int(kind), _p(x), _p(y), I64(len(x)),
                                      C.c_int(threads), C.byref(chk))
     return int(k), int(chk.value)
+
+
+# ---------------------------------------------------------------- iterated local search
+def nq_ils(seed, chain, n, kind=SWAP, ls_max_iterations=10_000, allow_no_improvement_for=5,
+           rounds=100, best_cap=32):
+    """IteratedLocalSearch (iterated_local_search.rs:173-202) restated; see cs_oracle.c."""
+    best = np.zeros(max(n, 1), dtype=np.int64)
+    cur = np.zeros(max(n, 1), dtype=np.int64)
+    rn = np.zeros(max(rounds, 1), dtype=np.int64)
+    rc = np.zeros(max(rounds, 1), dtype=np.int64)
+    bs = I64(0)
+    r = lib().orc_nq_ils(U64(seed), C.c_uint32(chain), I64(n), C.c_int(kind), U64(ls_max_iterations),
+                         U64(allow_no_improvement_for), U64(rounds), C.c_int(best_cap), _p(best),
+                         C.byref(bs), _p(cur), _p(rn), _p(rc))
+    r = int(r)
+    return dict(rounds=r, best=best[:n], best_score=int(bs.value), current=cur[:n],
+                round_new_score=rn[:r], round_choice=rc[:r])
+
+
+def es_ils(seed, chain, D, employees, start_weekday=0, holidays=None, ls_max_iterations=1000,
+           allow_no_improvement_for=20, rounds=50, best_cap=64):
+    employees = _i64(employees)
+    he, hd = _hol(holidays)
+    best = np.zeros(D + 1, dtype=np.int64)
+    rn = np.zeros(max(rounds, 1), dtype=np.int64)
+    rc = np.zeros(max(rounds, 1), dtype=np.int64)
+    bh, bs = I64(0), I64(0)
+    r = lib().orc_es_ils(U64(seed), C.c_uint32(chain), I64(D), C.c_int(start_weekday), _p(he), _p(hd),
+                         I64(len(he)), _p(employees), I64(len(employees)), U64(ls_max_iterations),
+                         U64(allow_no_improvement_for), U64(rounds), C.c_int(best_cap), _p(best),
+                         C.byref(bh), C.byref(bs), _p(rn), _p(rc))
+    r = int(r)
+    return dict(rounds=r, best=employees[best], best_hard=int(bh.value), best_soft=int(bs.value),
+                round_new_key=rn[:r], round_choice=rc[:r])
