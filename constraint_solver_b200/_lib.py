@@ -24,6 +24,7 @@ CS_NQ_SWAP, CS_NQ_CHANGE = 0, 1
 CS_NQ_MAX_N_SMEM = 16384
 CS_NQ_MAX_N = 1_000_000
 CS_NQ_FLAG_GLOBAL = 1
+CS_NQ_FLAG_SCALAR = 2
 CHAIN_RUNNING, CHAIN_BEST, CHAIN_STALLED, CHAIN_EMPTY = 0, 1, 2, 3
 PHILOX_INIT, PHILOX_PERTURB, PHILOX_ACCEPT, PHILOX_HOLIDAYS = 0, 1, 2, 3
 

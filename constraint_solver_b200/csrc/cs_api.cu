@@ -11,6 +11,7 @@
 #include "../../include/cs_b200.h"
 #include "nq_kernels.cuh"
 #include "nq_big.cuh"
+#include "nq_packed.cuh"
 #include "ils_kernels.cuh"
 #include "philox.cuh"
 
@@ -118,6 +119,9 @@ struct cs_nq_handle {
     int sm_count = 0;
     int threads = NQ_THREADS;
     size_t smem = 0;
+    bool use_v2 = false;   // step kernel with the packed-window fast path
+    size_t smem_v2 = 0;
+    int grid_v2 = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint16_t* d_rows = nullptr;
@@ -228,6 +232,18 @@ void nq_refresh_stats(cs_nq_handle* h) {
                        h->stream));
 }
 
+void nq_launch_step(cs_nq_handle* h, NqParams& p, int count) {
+    p.force_scalar = (h->cfg.flags & CS_NQ_FLAG_SCALAR) ? 1 : 0;
+    if (h->use_v2) {
+        const int grid = count < h->grid_v2 ? count : h->grid_v2;
+        nq_step_kernel_v2<NQ_TI><<<grid, NQC_THREADS, h->smem_v2, h->stream>>>(p);
+    } else {
+        const int grid = count < h->sm_count ? count : h->sm_count;
+        nq_step_kernel<NQ_TI><<<grid, h->threads, h->smem, h->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+}
+
 void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
             unsigned long long allow, int ls_mode, cs_step_stats* stats) {
     if (!h->scored) throw StateFail{"chains have no solution yet: call cs_nq_init_random or cs_nq_set_chains first"};
@@ -237,10 +253,8 @@ void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
     p.ls_mode = ls_mode;
     CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
     CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
-    const int grid = count < h->sm_count ? count : h->sm_count;
     CU(cudaEventRecord(h->ev0, h->stream));
-    nq_step_kernel<NQ_TI><<<grid, h->threads, h->smem, h->stream>>>(p);
-    CU(cudaGetLastError());
+    nq_launch_step(h, p, count);
     nq_refresh_stats(h);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
@@ -369,7 +383,16 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nq_step_kernel<NQ_TI>,
                                                          h->threads, h->smem));
         if (per_sm < 1) per_sm = 1;
+        h->grid_v2 = h->sm_count;
         h->sm_count *= per_sm;  // sm_count now = resident CTA slots (grid cap)
+        h->use_v2 = cfg->neighbourhood == CS_NQ_SWAP && n >= NQC_MIN_N && n <= NQC_MAX_N;
+        if (h->use_v2) {
+            const size_t a = nq_smem_bytes_v2(h->n_pad), c = nqc_smem_bytes(h->n_pad);
+            h->smem_v2 = a > c ? a : c;
+            REQUIRE(h->smem_v2 <= (size_t)prop.sharedMemPerBlockOptin, "packed layout does not fit");
+            CU(cudaFuncSetAttribute(nq_step_kernel_v2<NQ_TI>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_v2));
+        }
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
         const size_t nc = cfg->n_chains;
@@ -645,8 +668,7 @@ extern "C" int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, i
                 p.max_steps = 1;
                 p.dump = d_dump;
                 CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-                nq_step_kernel<NQ_TI><<<1, h->threads, h->smem, h->stream>>>(p);
-                CU(cudaGetLastError());
+                nq_launch_step(h, p, 1);
             }
             CU(cudaMemcpyAsync(delta, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost,
                                h->stream));
@@ -828,7 +850,6 @@ extern "C" int32_t cs_nq_ils_run(cs_nq_handle* h, uint32_t rounds, uint64_t ls_m
         lp.allow_no_improve = allow;
         lp.ls_mode = 1;
         lp.skip = h->ils.d_skip;
-        const int ls_grid = nc < h->sm_count ? nc : h->sm_count;
         const int ig = ils_grid(nc, h->sm_count);
         unsigned launches = 0, run = 0;
         CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
@@ -836,7 +857,7 @@ extern "C" int32_t cs_nq_ils_run(cs_nq_handle* h, uint32_t rounds, uint64_t ls_m
         for (uint32_t r = 0; r < rounds; ++r) {
             ils_perturb_kernel<<<ig, ILS_THREADS, h->ils.perturb_smem, h->stream>>>(ip);
             CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-            nq_step_kernel<NQ_TI><<<ls_grid, h->threads, h->smem, h->stream>>>(lp);
+            nq_launch_step(h, lp, nc);
             nq_gather_keys_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_st, h->ils.d_neu_key,
                                                                              nullptr, nc);
             ils_accept_kernel<<<ig, ILS_THREADS, 0, h->stream>>>(ip);

@@ -57,6 +57,7 @@ struct NqParams {
     int kind;                             // 0 swap, 1 change
     long long* dump;                      // debug: every candidate delta (one chain)
     const unsigned int* skip;             // optional [chains]: 1 = leave the chain alone (ILS)
+    int force_scalar;                     // v2 kernel: never take the packed path
 };
 
 // ------------------------------------------------------------------ shared memory view

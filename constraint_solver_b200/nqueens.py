@@ -90,7 +90,7 @@ class NQueensChains:
 
     def __init__(self, n: int, n_chains: int = 1, *, seed: int = 42, chain_offset: int = 0,
                  neighbourhood: int = SWAP, trace_capacity: int = 0, device: int = -1,
-                 force_global: bool = False):
+                 force_global: bool = False, force_scalar: bool = False):
         self._lib = L.load()
         self.n, self.n_chains = int(n), int(n_chains)
         self.neighbourhood = neighbourhood
@@ -99,7 +99,8 @@ class NQueensChains:
         cfg = L.CsNqConfig(n=n, n_chains=n_chains, chain_offset=chain_offset,
                            trace_capacity=trace_capacity, seed=seed, device=device,
                            neighbourhood=neighbourhood,
-                           flags=L.CS_NQ_FLAG_GLOBAL if force_global else 0)
+                           flags=(L.CS_NQ_FLAG_GLOBAL if force_global else 0)
+                           | (L.CS_NQ_FLAG_SCALAR if force_scalar else 0))
         h = C.c_void_p()
         rc = self._lib.cs_nq_create(C.byref(cfg), C.byref(h))
         if rc != L.CS_OK:

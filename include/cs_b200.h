@@ -47,6 +47,7 @@ extern "C" {
  * one instance per handle, swap neighbourhood, optionally partitioned across handles/GPUs. */
 #define CS_NQ_MAX_N 1000000u
 #define CS_NQ_FLAG_GLOBAL 1u /* force the global-memory (big board) path for any n */
+#define CS_NQ_FLAG_SCALAR 2u /* never use the packed-window fast scan (parity / A-B testing) */
 
 /* neighbourhood kinds */
 #define CS_NQ_SWAP 0u   /* exchange rows of columns i<j (new; defined against lib.rs:74-87) */
