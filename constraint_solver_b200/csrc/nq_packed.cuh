@@ -35,6 +35,7 @@ constexpr int NQC_MIN_N = 256;
 constexpr int NQC_MAX_N = 12096;
 constexpr int NQC_THREADS = 512;
 constexpr int NQC_INF16 = 0x3fff;
+constexpr int NQC_BIAS = 128;       // keeps X - c_j + 7 positive in each 16-bit half (c_j <= 124)
 
 struct NqSmemC {
     int* red;        // [128]
@@ -176,7 +177,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
         const int i0 = t * TI;  // multiple of 8
         // per-slot lane-consecutive read offsets (copy fixed by the slot's row, word = 4*lane)
         int pv1[TI], pv2[TI];
-        unsigned U[TI / 2], Wd[TI / 2], m[TI / 2];
+        unsigned NU[TI / 2], NW[TI / 2], m[TI / 2];  // complemented diagonal ids: x ^ ~y == ~(x ^ y)
 #pragma unroll
         for (int p = 0; p < TI / 2; ++p) {
             unsigned uu = 0, ww = 0;
@@ -190,8 +191,8 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 uu |= (unsigned)((2 * (ri - i)) & 0xffff) << (16 * h);
                 ww |= (unsigned)((2 * (ri + i)) & 0xffff) << (16 * h);
             }
-            U[p] = uu;
-            Wd[p] = ww;
+            NU[p] = ~uu;
+            NW[p] = ~ww;
             m[p] = (unsigned)NQC_INF16 * 0x10001u;
         }
         const int A1 = i0 + n - 1, A2 = i0;
@@ -229,16 +230,18 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 const unsigned char* g2 = smem0 + q2off + (t2 & 3) * ldb + (t2 & ~3);
                 const unsigned Xlo = *(const unsigned*)g1 + *(const unsigned*)g2 + TP[b][0];
                 const unsigned Xhi = *(const unsigned*)(g1 + 4) + *(const unsigned*)(g2 + 4) + TP[b][1];
-                const unsigned kj = bcast16((unsigned)(7 - cj) & 0xffffu);
-                const unsigned ub = bcast16((unsigned)(2 * (rj - j)) & 0xffffu);
-                const unsigned wb = bcast16((unsigned)(2 * (rj + j)) & 0xffffu);
+                // bcast16 takes the low 16 bits; kj is biased by NQC_BIAS so both halves stay
+                // positive and the packed add below is a plain 32-bit add (no inter-half carry)
+                const unsigned kj = bcast16((unsigned)(7 + NQC_BIAS - cj));
+                const unsigned ub = bcast16((unsigned)(2 * (rj - j)));
+                const unsigned wb = bcast16((unsigned)(2 * (rj + j)));
 #pragma unroll
                 for (int p = 0; p < TI / 2; ++p) {
                     const unsigned src = (p < 2) ? Xlo : Xhi;
                     const unsigned x16 = __byte_perm(src, 0u, (p & 1) ? 0x4342 : 0x4140);
-                    unsigned y = __vadd2(x16, kj);
+                    unsigned y = x16 + kj;
                     // att: equal diagonal ids -> XNOR = 0xFFFF (= -1), else <= 0xFFFD (= -3)
-                    const unsigned a2 = __vimax3_u16x2(~(ub ^ U[p]), ~(wb ^ Wd[p]), 0xFFFDFFFDu);
+                    const unsigned a2 = __vimax3_u16x2(ub ^ NU[p], wb ^ NW[p], 0xFFFDFFFDu);
                     if (masked) {
                         const int ia = i0 + 2 * p;
                         unsigned pen = 0;
@@ -253,7 +256,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                             const int i = i0 + 2 * p + h;
                             if (j > i && j < n) {
                                 const int zz = (int)(short)((z >> (16 * h)) & 0xffff);
-                                dump[nq_swap_index(n, i, j)] = 2ll * (long long)(zz - (int)s.cb[i]);
+                                dump[nq_swap_index(n, i, j)] = 2ll * (long long)(zz - NQC_BIAS - (int)s.cb[i]);
                             }
                         }
                     }
@@ -266,7 +269,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
         chunk(jc, true);
         jc += NQC_CHUNK;
         const int jm1 = n & ~(NQC_CHUNK - 1);
-#pragma unroll 1
+#pragma unroll 2
         for (; jc < jm1; jc += NQC_CHUNK) chunk(jc, false);
         if (jc < n) chunk(jc, true);
 
@@ -277,7 +280,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 const int i = i0 + 2 * p + h;
                 const int mv = (int)(short)((m[p] >> (16 * h)) & 0xffff);
                 if (i < n - 1 && mv < NQC_INF16 / 2) {
-                    const int v = mv - (int)s.cb[i];
+                    const int v = mv - NQC_BIAS - (int)s.cb[i];
                     if (v < best_v) {
                         best_v = v;
                         best_i = (unsigned)i;
