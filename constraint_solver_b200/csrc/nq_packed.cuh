@@ -35,6 +35,7 @@ constexpr int NQC_MIN_N = 256;
 constexpr int NQC_MAX_N = 12096;
 constexpr int NQC_THREADS = 512;
 constexpr int NQC_INF16 = 0x3fff;
+constexpr int NQC_UBIAS = 32768;    // 2*(r - c) + UBIAS is a positive 16-bit id for |r - c| < 16384
 constexpr int NQC_BIAS = 128;       // keeps X - c_j + 7 positive in each 16-bit half (c_j <= 124)
 
 struct NqSmemC {
@@ -167,7 +168,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int num_tiles = (n - 1 + TI - 1) / TI;
     const unsigned char* smem0 = (const unsigned char*)s.Q1;  // Q2 = Q1 + 4*ldb
-    const int ldb = s.ldb, q2off = 4 * s.ldb;
+    const int ldbm1 = s.ldb - 1, q2off = 4 * s.ldb;
     best_v = NQ_INF;
     best_i = 0xffffffffu;
 
@@ -175,6 +176,8 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
         const int t = k * W + ((k & 1) ? (W - 1 - w) : w);
         if (t >= num_tiles) continue;
         const int i0 = t * TI;  // multiple of 8
+        const int jbase = i0 & ~(NQC_CHUNK - 1);  // first chunk (holds the tile); the loop
+                                                  // offset dj below is warp-uniform by construction
         // per-slot lane-consecutive read offsets (copy fixed by the slot's row, word = 4*lane)
         int pv1[TI], pv2[TI];
         unsigned NU[TI / 2], NW[TI / 2], m[TI / 2];  // complemented diagonal ids: x ^ ~y == ~(x ^ y)
@@ -186,9 +189,10 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 const int a = 2 * p + h, i = i0 + a;
                 const int ri = s.rows[i];  // padded read for i >= n (masked later)
                 const int x1 = n - 1 - ri, x2 = ri;
-                pv1[a] = (x1 & 3) * ldb + (x1 & ~3) + 4 * lane;
-                pv2[a] = q2off + (x2 & 3) * ldb + (x2 & ~3) + 4 * lane;
-                uu |= (unsigned)((2 * (ri - i)) & 0xffff) << (16 * h);
+                // copy (x & 3), word (x & ~3):  (x & 3) * ldb + (x & ~3) == x + (x & 3) * (ldb - 1)
+                pv1[a] = x1 + (x1 & 3) * ldbm1 + 4 * lane + jbase;
+                pv2[a] = q2off + x2 + (x2 & 3) * ldbm1 + 4 * lane + jbase;
+                uu |= (unsigned)((2 * (ri - i) + NQC_UBIAS) & 0xffff) << (16 * h);
                 ww |= (unsigned)((2 * (ri + i)) & 0xffff) << (16 * h);
             }
             NU[p] = ~uu;
@@ -197,15 +201,18 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
         }
         const int A1 = i0 + n - 1, A2 = i0;
 
-        auto chunk = [&](int jc, bool masked) {
+        const unsigned char* rowp = (const unsigned char*)(s.rows + jbase + NQC_TJ * lane);
+        const unsigned char* cbp = (const unsigned char*)(s.cb + jbase + NQC_TJ * lane);
+        auto chunk = [&](int dj, bool masked) {
+            const int jc = jbase + dj;
             const int j0 = jc + NQC_TJ * lane;
-            const uint2 r4 = *(const uint2*)(s.rows + j0);     // 4 rows (u16)
-            const unsigned c4 = *(const unsigned*)(s.cb + j0);  // 4 c_j bytes
+            const uint2 r4 = *(const uint2*)(rowp + 2 * dj);  // 4 rows (u16)
+            const unsigned c4 = *(const unsigned*)(cbp + dj);  // 4 c_j bytes
             // lane-consecutive windows: T[a] = D1[j0..j0+3 - r_ia] + D2[j0..j0+3 + r_ia]
             unsigned T[TI];
 #pragma unroll
             for (int a = 0; a < TI; ++a)
-                T[a] = *(const unsigned*)(smem0 + pv1[a] + jc) + *(const unsigned*)(smem0 + pv2[a] + jc);
+                T[a] = *(const unsigned*)(smem0 + pv1[a] + dj) + *(const unsigned*)(smem0 + pv2[a] + dj);
             // transpose bytes: TP[b][0] = slots 0..3 at j_b, TP[b][1] = slots 4..7 at j_b
             unsigned TP[NQC_TJ][2];
 #pragma unroll
@@ -226,15 +233,16 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 const int cj = (int)(c4 >> (8 * b)) & 0xff;
                 // data-dependent windows over the 8 column slots
                 const int t1 = A1 - rj, t2 = A2 + rj;
-                const unsigned char* g1 = smem0 + (t1 & 3) * ldb + (t1 & ~3);
-                const unsigned char* g2 = smem0 + q2off + (t2 & 3) * ldb + (t2 & ~3);
+                const unsigned char* g1 = smem0 + t1 + (t1 & 3) * ldbm1;
+                const unsigned char* g2 = smem0 + q2off + t2 + (t2 & 3) * ldbm1;
                 const unsigned Xlo = *(const unsigned*)g1 + *(const unsigned*)g2 + TP[b][0];
                 const unsigned Xhi = *(const unsigned*)(g1 + 4) + *(const unsigned*)(g2 + 4) + TP[b][1];
                 // bcast16 takes the low 16 bits; kj is biased by NQC_BIAS so both halves stay
                 // positive and the packed add below is a plain 32-bit add (no inter-half carry)
-                const unsigned kj = bcast16((unsigned)(7 + NQC_BIAS - cj));
-                const unsigned ub = bcast16((unsigned)(2 * (rj - j)));
-                const unsigned wb = bcast16((unsigned)(2 * (rj + j)));
+                // positive 16-bit values broadcast to both halves by a multiply (FMA pipe, no PRMT)
+                const unsigned kj = (unsigned)(7 + NQC_BIAS - cj) * 0x10001u;
+                const unsigned ub = (unsigned)(2 * (rj - j) + NQC_UBIAS) * 0x10001u;
+                const unsigned wb = (unsigned)(2 * (rj + j)) * 0x10001u;
 #pragma unroll
                 for (int p = 0; p < TI / 2; ++p) {
                     const unsigned src = (p < 2) ? Xlo : Xhi;
@@ -265,13 +273,12 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
             }
         };
 
-        int jc = i0 & ~(NQC_CHUNK - 1);  // the chunk holding the tile: needs the j > i mask
-        chunk(jc, true);
-        jc += NQC_CHUNK;
-        const int jm1 = n & ~(NQC_CHUNK - 1);
+        chunk(0, true);  // the chunk holding the tile: needs the j > i mask
+        const int dj_full = (n & ~(NQC_CHUNK - 1)) - jbase;  // end of the full chunks
+        int dj = NQC_CHUNK;
 #pragma unroll 2
-        for (; jc < jm1; jc += NQC_CHUNK) chunk(jc, false);
-        if (jc < n) chunk(jc, true);
+        for (; dj < dj_full; dj += NQC_CHUNK) chunk(dj, false);
+        if (jbase + dj < n) chunk(dj, true);
 
 #pragma unroll
         for (int p = 0; p < TI / 2; ++p)
