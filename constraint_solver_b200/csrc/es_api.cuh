@@ -18,6 +18,7 @@ struct cs_es_handle {
     uint16_t* d_a = nullptr;
     uint16_t* d_best_a = nullptr;
     u64* d_hol = nullptr;
+    u64* d_dayconst = nullptr;  // [3][64] PART, CONT14, CONT7
     EsChainState* d_st = nullptr;
     EsTraceEntry* d_trace = nullptr;
     unsigned int* d_work = nullptr;
@@ -44,6 +45,7 @@ EsParams es_params(cs_es_handle* h, int first, int count) {
     p.a = h->d_a;
     p.best_a = h->d_best_a;
     p.hol = h->d_hol;
+    p.dayconst = h->d_dayconst;
     p.st = h->d_st;
     p.trace = h->d_trace;
     p.trace_cap = (int)h->cfg.trace_capacity;
@@ -59,6 +61,7 @@ void es_free(cs_es_handle* h) {
     cudaFree(h->d_a);
     cudaFree(h->d_best_a);
     cudaFree(h->d_hol);
+    cudaFree(h->d_dayconst);
     cudaFree(h->d_st);
     cudaFree(h->d_trace);
     cudaFree(h->d_work);
@@ -218,6 +221,24 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
             if (w >= 5) K.wkend |= 1ull << d;
             if (w == 5 && d + 9 <= D) K.satf |= 1ull << d;  // windows(9) start, lib.rs:295-302
         }
+        // per-day constants of the hot loop: H2/H3 partner days and the window starts holding d
+        std::vector<u64> dayc(3 * 64, 0ull);
+        for (int d = 0; d < D; ++d) {
+            if (d > 0) dayc[d] |= 1ull << (d - 1);          // H2, lib.rs:286-292
+            if (d + 1 < D) dayc[d] |= 1ull << (d + 1);
+            for (int w = 0; w < K.n14; ++w)
+                if (w <= d && d <= w + 13) dayc[64 + d] |= 1ull << w;
+            for (int w = 0; w < K.n7; ++w)
+                if (w <= d && d <= w + 6) dayc[128 + d] |= 1ull << w;
+        }
+        for (int sat = 0; sat < D; ++sat) {                 // H3, lib.rs:295-315
+            if (!((K.satf >> sat) & 1ull)) continue;
+            const int pr[4][2] = {{sat, sat + 7}, {sat, sat + 8}, {sat + 1, sat + 7}, {sat + 1, sat + 8}};
+            for (auto& q : pr) {
+                dayc[q[0]] |= 1ull << q[1];
+                dayc[q[1]] |= 1ull << q[0];
+            }
+        }
         std::vector<u64> hol(E, 0ull);
         for (uint64_t k = 0; k < n_hol; ++k) {
             const int idx = es_index_of(h, hol_emp[k]);
@@ -242,6 +263,7 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         CU(cudaMalloc(&h->d_a, nc * h->stride * sizeof(uint16_t)));
         CU(cudaMalloc(&h->d_best_a, nc * h->stride * sizeof(uint16_t)));
         CU(cudaMalloc(&h->d_hol, (size_t)E * sizeof(u64)));
+        CU(cudaMalloc(&h->d_dayconst, dayc.size() * sizeof(u64)));
         CU(cudaMalloc(&h->d_st, nc * sizeof(EsChainState)));
         if (cfg->trace_capacity)
             CU(cudaMalloc(&h->d_trace, nc * cfg->trace_capacity * sizeof(EsTraceEntry)));
@@ -255,6 +277,7 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         CU(cudaEventCreate(&h->ev0));
         CU(cudaEventCreate(&h->ev1));
         CU(cudaMemcpyAsync(h->d_hol, hol.data(), (size_t)E * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_dayconst, dayc.data(), dayc.size() * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemsetAsync(h->d_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));
         CU(cudaMemsetAsync(h->d_best_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));
         es_reset_state_kernel<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>(h->d_st, 0, (int)nc);

@@ -13,6 +13,13 @@
 //   S1_e = #{w : popc(m & W7<<w)  > 2}                           (:330-339)
 // so a move's delta on these terms is F(m') - F(m) over the (at most two) employees whose
 // mask changes, with the window loops restricted to windows that overlap a changed day.
+// Hot-loop formulation (es_prepare + es_change_delta / es_swap_delta): once per chain-step,
+// for every PRESENT employee (<= D of them) all sliding-window counts are computed at once by a
+// bit-sliced adder over the day mask, kept as "count == k" window-start masks
+// (EQ3_14, EQ4_14, EQ2_7, EQ3_7); per day d the terms that only depend on the day's current
+// employee are tabulated.  A candidate then needs three 64-bit popcounts for H2+H3, H4 and S1:
+//   gain of day d for employee e = popc(m_e & PART[d]) + popc(EQ3_14[e] & CONT14[d]) ...
+// where PART[d] = days paired with d by H2/H3 and CONT[d] = window starts whose window holds d.
 // S2 (weekday affinity, min over employees present on that weekday), S3 (max-min of total
 // days over PRESENT employees) and S4 (max-min of weekend days over present employees) are
 // kept as count histograms + occupancy bitsets, so min/max after a move are bit scans.
@@ -55,6 +62,7 @@ struct EsParams {
     uint16_t* a;                        // [*, stride] employee index per slot
     uint16_t* best_a;
     const u64* hol;  // [E] holiday day-mask per employee
+    const u64* dayconst;  // [3][64]: PART (H2/H3 partner days), CONT14, CONT7 (window starts holding d)
     EsChainState* st;
     EsTraceEntry* trace;
     int trace_cap;
@@ -79,6 +87,12 @@ struct EsSmem {
     unsigned int* occW; // [1]  bit c: some PRESENT employee has exactly c weekend days (c>=0)
     int* misc;          // [16] present, distinct[5], hard, soft, ...
     u64* red;           // [40] reduction scratch
+    u64* part;          // [64] H2/H3 partner-day mask per day
+    u64* cont14;        // [64] 14-day window starts whose window contains the day
+    u64* cont7;         // [64]
+    u64* eq;            // [64][4] per present-employee slot: EQ3_14, EQ4_14, EQ2_7, EQ3_7
+    unsigned char* dayb;   // [5][64] per day, for its current employee: lossH, lossS1, total, weekend, weekday count
+    unsigned char* pslot;  // [E] present-employee slot (0xFF = absent)
 };
 
 __host__ __device__ inline size_t es_smem_bytes(int D, int E) {
@@ -92,6 +106,8 @@ __host__ __device__ inline size_t es_smem_bytes(int D, int E) {
     b += 8;                                         // occT
     b += 16 * 4;                                    // misc
     b += 40 * 8;                                    // red
+    b += 3 * 64 * 8 + 64 * 4 * 8 + 5 * 64;          // part, cont14, cont7, eq, dayb
+    b += (size_t)(E + 7) / 8 * 8;                   // pslot
     return b;
 }
 
@@ -116,10 +132,20 @@ __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     s.misc = (int*)p;
     p += 16 * 4;
     s.red = (u64*)p;
+    p += 40 * 8;
+    s.part = (u64*)p;
+    s.cont14 = s.part + 64;
+    s.cont7 = s.cont14 + 64;
+    s.eq = s.cont7 + 64;
+    p += 3 * 64 * 8 + 64 * 4 * 8;
+    s.dayb = p;
+    p += 5 * 64;
+    s.pslot = p;
     return s;
 }
 
-enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8 };
+enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10 };
+enum { ES_DB_LOSSH = 0, ES_DB_LOSSS = 64, ES_DB_TOT = 128, ES_DB_WK = 192, ES_DB_WD = 256 };
 
 // ------------------------------------------------------------------ per-employee terms
 __device__ __forceinline__ int es_pair_terms(u64 m, u64 hol, const EsConst& K) {
@@ -166,29 +192,34 @@ __device__ __forceinline__ void es_emp_delta(u64 m, u64 m2, u64 hol, const EsCon
 }
 
 // ------------------------------------------------------------------ histogram helpers
+// up to four (bin, +-1) histogram adjustments, always four slots so everything stays in
+// registers (unused slots carry delta 0 on a valid bin)
 struct EsAdj {
-    int bin[4], d[4], n;
-    __device__ __forceinline__ EsAdj() : n(0) {}
+    int b0, b1, b2, b3, d0, d1, d2, d3, n;
+    __device__ __forceinline__ EsAdj() : b0(0), b1(0), b2(0), b3(0), d0(0), d1(0), d2(0), d3(0), n(0) {}
     __device__ __forceinline__ void add(int b, int delta) {
-        bin[n] = b;
-        d[n] = delta;
+        if (n == 0) { b0 = b; d0 = delta; }
+        else if (n == 1) { b1 = b; d1 = delta; }
+        else if (n == 2) { b2 = b; d2 = delta; }
+        else { b3 = b; d3 = delta; }
         ++n;
     }
 };
 
+__device__ __forceinline__ u64 es_occ_one(const uint16_t* hist, u64 occ, int b, const EsAdj& A) {
+    const int tot = (A.b0 == b ? A.d0 : 0) + (A.b1 == b ? A.d1 : 0) + (A.b2 == b ? A.d2 : 0) +
+                    (A.b3 == b ? A.d3 : 0);
+    const int c = (int)hist[b] + tot;
+    const u64 bit = 1ull << b;
+    return c > 0 ? (occ | bit) : (occ & ~bit);
+}
+
 // occupancy bitset after applying the adjustments to the histogram
 __device__ __forceinline__ u64 es_occ_after(const uint16_t* hist, u64 occ, const EsAdj& A) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k >= A.n) break;
-        int tot = 0;
-#pragma unroll
-        for (int l = 0; l < 4; ++l)
-            if (l < A.n && A.bin[l] == A.bin[k]) tot += A.d[l];
-        const int c = (int)hist[A.bin[k]] + tot;
-        const u64 bit = 1ull << A.bin[k];
-        occ = c > 0 ? (occ | bit) : (occ & ~bit);
-    }
+    occ = es_occ_one(hist, occ, A.b0, A);
+    occ = es_occ_one(hist, occ, A.b1, A);
+    occ = es_occ_one(hist, occ, A.b2, A);
+    occ = es_occ_one(hist, occ, A.b3, A);
     return occ;
 }
 
@@ -223,23 +254,88 @@ __device__ __forceinline__ int es_s2_delta(const EsSmem& s, int wd, int cm, int 
 
 __device__ __forceinline__ int es_weekday(const EsConst& K, int d) { return (K.start_wd + d) % 7; }
 
+// ------------------------------------------------------------------ per-step tables
+// All sliding-window counts of one day mask at once: bit-sliced adder over the L shifted
+// copies of m; plane i bit w = bit i of popc(m & (ONES(L) << w)).
+template <int L, int PLANES>
+__device__ __forceinline__ void es_window_planes(u64 m, u64 (&pl)[PLANES]) {
+#pragma unroll
+    for (int i = 0; i < PLANES; ++i) pl[i] = 0;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+        u64 carry = m >> k;
+#pragma unroll
+        for (int i = 0; i < PLANES; ++i) {
+            const u64 t = pl[i] & carry;
+            pl[i] ^= carry;
+            carry = t;
+        }
+    }
+}
+
+// Once per chain-step (masks must be current): present-employee slots, their "count == k"
+// window masks, and the per-day tables of the day's current employee.  Block-cooperative.
+__device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) s.misc[ES_NSLOT] = 0;
+    __syncthreads();
+    const u64 v14 = K.n14 >= 64 ? ~0ull : ((1ull << K.n14) - 1);  // real window starts only
+    const u64 v7 = K.n7 >= 64 ? ~0ull : ((1ull << K.n7) - 1);
+    for (int e = tid; e < K.E; e += nt) {
+        const u64 m = s.mask[e];
+        if (!m) {
+            s.pslot[e] = 0xFF;
+            continue;
+        }
+        const int slot = atomicAdd(&s.misc[ES_NSLOT], 1);
+        s.pslot[e] = (unsigned char)slot;
+        u64 p14[4], p7[3];
+        es_window_planes<14, 4>(m, p14);
+        es_window_planes<7, 3>(m, p7);
+        u64* q = s.eq + slot * 4;
+        q[0] = p14[0] & p14[1] & ~p14[2] & ~p14[3] & v14;   // count == 3 (one more => H4 violation)
+        q[1] = ~p14[0] & ~p14[1] & p14[2] & ~p14[3] & v14;  // count == 4 (one less => violation gone)
+        q[2] = ~p7[0] & p7[1] & ~p7[2] & v7;                // count == 2
+        q[3] = p7[0] & p7[1] & ~p7[2] & v7;                 // count == 3
+    }
+    __syncthreads();
+    for (int d = tid; d < K.D; d += nt) {
+        const int eo = s.a[d];
+        const u64 m = s.mask[eo];
+        const u64* q = s.eq + (int)s.pslot[eo] * 4;
+        const int wd = (K.start_wd + d) % 7;
+        s.dayb[ES_DB_LOSSH + d] = (unsigned char)(((hol[eo] >> d) & 1ull) + __popcll(m & s.part[d]) +
+                                                  __popcll(q[1] & s.cont14[d]));
+        s.dayb[ES_DB_LOSSS + d] = (unsigned char)__popcll(q[3] & s.cont7[d]);
+        s.dayb[ES_DB_TOT + d] = (unsigned char)__popcll(m);
+        s.dayb[ES_DB_WK + d] = (unsigned char)__popcll(m & K.wkend);
+        s.dayb[ES_DB_WD + d] = (unsigned char)(wd < 5 ? __popcll(m & K.wd[wd]) : 0);
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ move deltas
 // change: day d gets employee en (!= current).  Returns (dhard, dsoft).
 __device__ __forceinline__ void es_change_delta(const EsSmem& s, const EsConst& K,
                                                 const u64* __restrict__ hol, int d, int en,
                                                 int& dh, int& ds) {
-    const int eo = s.a[d];
     const u64 bit = 1ull << d;
-    const u64 mo = s.mask[eo], mn = s.mask[en];
-    dh = 0;
-    ds = 0;
-    es_emp_delta(mo, mo & ~bit, hol[eo], K, dh, ds);
-    es_emp_delta(mn, mn | bit, hol[en], K, dh, ds);
+    const u64 mn = s.mask[en];
+    dh = (int)((hol[en] >> d) & 1ull) - (int)s.dayb[ES_DB_LOSSH + d];
+    ds = -(int)s.dayb[ES_DB_LOSSS + d];
+    int tn = 0, wn = 0, cn = 0;
     const int wd = es_weekday(K, d);
-    if (wd < 5) ds += es_s2_delta(s, wd, __popcll(mo & K.wd[wd]), __popcll(mn & K.wd[wd]));
+    if (mn) {  // an absent employee has no pairs and no window counts
+        const u64* q = s.eq + (int)s.pslot[en] * 4;
+        dh += __popcll(mn & s.part[d]) + __popcll(q[0] & s.cont14[d]);
+        ds += __popcll(q[2] & s.cont7[d]);
+        tn = __popcll(mn);
+        wn = __popcll(mn & K.wkend);
+        if (wd < 5) cn = __popcll(mn & K.wd[wd]);
+    }
+    if (wd < 5) ds += es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], cn);
     // S3 / S4 over present employees
-    const int to = __popcll(mo), tn = __popcll(mn);
-    const int wo = __popcll(mo & K.wkend), wn = __popcll(mn & K.wkend);
+    const int to = s.dayb[ES_DB_TOT + d], wo = s.dayb[ES_DB_WK + d];
     const int isw = (K.wkend & bit) ? 1 : 0;
     int present = s.misc[ES_PRESENT];
     const int oldT = es_spread(*s.occT, present), oldW = es_spread((u64)*s.occW, present);
@@ -270,12 +366,24 @@ __device__ __forceinline__ void es_swap_delta(const EsSmem& s, const EsConst& K,
                                               const u64* __restrict__ hol, int d1, int d2, int& dh,
                                               int& ds) {
     const int e1 = s.a[d1], e2 = s.a[d2];
-    const u64 b1 = 1ull << d1, b2 = 1ull << d2, x = b1 | b2;
+    const u64 b1 = 1ull << d1, b2 = 1ull << d2;
     const u64 m1 = s.mask[e1], m2 = s.mask[e2];
-    dh = 0;
-    ds = 0;
-    es_emp_delta(m1, m1 ^ x, hol[e1], K, dh, ds);
-    es_emp_delta(m2, m2 ^ x, hol[e2], K, dh, ds);
+    const u64* q1 = s.eq + (int)s.pslot[e1] * 4;
+    const u64* q2 = s.eq + (int)s.pslot[e2] * 4;
+    const u64 h1 = hol[e1], h2 = hol[e2];
+    // windows holding exactly one of the two days change count by one for each employee
+    const u64 c14a = s.cont14[d1], c14b = s.cont14[d2], c7a = s.cont7[d1], c7b = s.cont7[d2];
+    const u64 only14a = c14a & ~c14b, only14b = c14b & ~c14a, only7a = c7a & ~c7b, only7b = c7b & ~c7a;
+    dh = (int)((h1 >> d2) & 1ull) - (int)((h1 >> d1) & 1ull) + (int)((h2 >> d1) & 1ull) -
+         (int)((h2 >> d2) & 1ull);
+    // H2/H3 pairs: e1 leaves d1 and lands on d2 (its other days: m1 without d1), e2 the reverse
+    dh += __popcll((m1 & ~b1) & s.part[d2]) - __popcll(m1 & s.part[d1]);
+    dh += __popcll((m2 & ~b2) & s.part[d1]) - __popcll(m2 & s.part[d2]);
+    // H4: e1 loses a day in windows with only d1 (count 4 -> 3), gains in windows with only d2
+    dh += __popcll(q1[0] & only14b) - __popcll(q1[1] & only14a);
+    dh += __popcll(q2[0] & only14a) - __popcll(q2[1] & only14b);
+    ds = __popcll(q1[2] & only7b) - __popcll(q1[3] & only7a);
+    ds += __popcll(q2[2] & only7a) - __popcll(q2[3] & only7b);
     const int wd1 = es_weekday(K, d1), wd2 = es_weekday(K, d2);
     if (wd1 != wd2) {
         // the two weekdays are distinct histograms, so their deltas are independent
@@ -431,6 +539,7 @@ __global__ void es_step_kernel(EsParams p) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int D = K.D, E = K.E;
     const int n_change = D * E, n_swap = D * (D - 1) / 2, n_moves = n_change + n_swap;
+    for (int k = tid; k < 192; k += nt) s.part[k] = p.dayconst[k];  // part | cont14 | cont7
 
     for (;;) {
         __syncthreads();
@@ -462,6 +571,7 @@ __global__ void es_step_kernel(EsParams p) {
                 best_s = 0;
                 break;
             }
+            es_prepare(s, K, p.hol);
             long long key = ES_KEY_INF;
             unsigned int nscored = 0;
             for (int id = tid; id < n_moves; id += nt) {
@@ -622,9 +732,11 @@ __global__ void es_eval_kernel(EsParams p, int chain, int kind, const uint2* __r
     const EsSmem s = es_carve(smem_raw, p.K.D, p.K.E);
     for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
         s.a[k] = p.a[(size_t)chain * p.stride + k];
+    for (int k = threadIdx.x; k < 192; k += blockDim.x) s.part[k] = p.dayconst[k];
     __syncthreads();
     int hard, soft;
     es_build(s, p.K, p.hol, hard, soft);
+    es_prepare(s, p.K, p.hol);
     for (unsigned long long k = threadIdx.x; k < n_moves; k += blockDim.x) {
         const uint2 mv = moves[k];
         int dh = 0, ds = 0;
