@@ -25,8 +25,9 @@ CS_NQ_MAX_N_SMEM = 16384
 CS_NQ_MAX_N = 1_000_000
 CS_NQ_FLAG_GLOBAL = 1
 CS_NQ_FLAG_SCALAR = 2
+CS_NQ_FLAG_REFERENCE_PROPOSER = 4
 CHAIN_RUNNING, CHAIN_BEST, CHAIN_STALLED, CHAIN_EMPTY = 0, 1, 2, 3
-PHILOX_INIT, PHILOX_PERTURB, PHILOX_ACCEPT, PHILOX_HOLIDAYS = 0, 1, 2, 3
+PHILOX_INIT, PHILOX_PERTURB, PHILOX_LS, PHILOX_HOLIDAYS = 0, 1, 2, 3
 
 
 class CsError(RuntimeError):
@@ -137,6 +138,7 @@ SIGNATURES = {
     "cs_nq_eval_moves": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, C.c_uint64, _VP]),
     "cs_nq_enumerate": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_nq_neighbourhood_deltas": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
+    "cs_nq_set_window": (C.c_int32, [_VP, C.c_uint64]),
     "cs_nq_step": (C.c_int32, [_VP, C.c_uint32, _P(CsStepStats)]),
     "cs_nq_local_search": (C.c_int32, [_VP, C.c_uint64, C.c_uint64, _P(CsStepStats)]),
     "cs_nq_get_best_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, _VP]),

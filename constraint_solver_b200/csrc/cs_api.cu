@@ -149,6 +149,9 @@ struct cs_nq_handle {
     uint32_t part = 0, parts = 1;
     unsigned long long ls_no_improve = 0;
     IlsHost ils;
+    bool ref_mode = false;
+    unsigned long long window = 0;
+    unsigned long long* d_ls_rng = nullptr;  // [chains] LS-owned rng draw counters
     std::string err;
 };
 
@@ -174,6 +177,11 @@ NqParams nq_params(cs_nq_handle* h, int first, int count) {
     p.ls_mode = 0;
     p.kind = (int)h->cfg.neighbourhood;
     p.dump = nullptr;
+    p.ref_mode = h->ref_mode ? 1 : 0;
+    p.window = h->window;
+    p.ls_rng_t = h->d_ls_rng;
+    p.seed = h->cfg.seed;
+    p.chain_offset = h->cfg.chain_offset;
     return p;
 }
 
@@ -190,6 +198,7 @@ void nq_free(cs_nq_handle* h) {
     cudaFree(h->d_stats);
     cudaFree(h->d_stage);
     cudaFree(h->d_bad);
+    cudaFree(h->d_ls_rng);
     if (h->is_big) {
         cudaFree(h->big.rows);
         cudaFree(h->big.c);
@@ -329,6 +338,8 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
     // the L2-resident path holds one instance per handle and scores the swap neighbourhood
     if (big && (cfg->n_chains != 1 || cfg->neighbourhood != CS_NQ_SWAP)) return CS_ERR_UNSUPPORTED;
     if ((uint64_t)cfg->chain_offset + cfg->n_chains > 0xffffffffull) return CS_ERR_INVALID_ARG;
+    const bool ref_mode = (cfg->flags & CS_NQ_FLAG_REFERENCE_PROPOSER) != 0;
+    if (ref_mode && (big || cfg->neighbourhood != CS_NQ_CHANGE)) return CS_ERR_UNSUPPORTED;
     int ndev = cs_device_count();
     if (ndev <= 0) return CS_ERR_NO_DEVICE;
     int dev = cfg->device;
@@ -369,6 +380,9 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
             return;
         }
         h->smem = nq_smem_bytes(h->n_pad);
+        h->ref_mode = ref_mode;
+        h->window = 5ull * cfg->n;  // examples/nqueens/src/main.rs:130
+        if (ref_mode) h->smem += (size_t)4 * h->n_pad;  // proposer scratch behind the layout
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin,
                 "board does not fit the shared-memory chain kernel on this device");
         h->threads = n <= 96 ? 128 : n <= 512 ? 256 : n <= 2048 ? 512 : 1024;
@@ -405,6 +419,8 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
         CU(cudaMalloc(&h->d_totals, 2 * sizeof(unsigned long long)));
         CU(cudaMalloc(&h->d_stats, sizeof(NqStats)));
         CU(cudaMalloc(&h->d_bad, sizeof(int)));
+        CU(cudaMalloc(&h->d_ls_rng, nc * sizeof(unsigned long long)));
+        CU(cudaMemset(h->d_ls_rng, 0, nc * sizeof(unsigned long long)));
         CU(cudaMallocHost(&h->h_stats, sizeof(NqStats)));
         CU(cudaMallocHost(&h->h_totals, 2 * sizeof(unsigned long long)));
         // staging for int64 <-> u16 conversion: whole chains, ~64 MiB or one chain
@@ -462,6 +478,7 @@ extern "C" int32_t cs_nq_init_random(cs_nq_handle* h) {
             return;
         }
         const int nc = (int)h->cfg.n_chains;
+        CU(cudaMemsetAsync(h->d_ls_rng, 0, (size_t)nc * sizeof(unsigned long long), h->stream));
         nq_init_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(h->d_rows, h->d_st, (int)h->cfg.n,
                                                               h->n_pad, nc, h->cfg.seed,
                                                               h->cfg.chain_offset);
@@ -485,6 +502,7 @@ extern "C" int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first, uint32_t co
             return;
         }
         nq_upload(h, first, count, rows);
+        CU(cudaMemsetAsync(h->d_ls_rng + first, 0, (size_t)count * sizeof(unsigned long long), h->stream));
         nq_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first,
                                                                           (int)count);
         CU(cudaGetLastError());
@@ -678,6 +696,13 @@ extern "C" int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, i
             throw;
         }
         cudaFree(d_dump);
+    });
+}
+
+extern "C" int32_t cs_nq_set_window(cs_nq_handle* h, uint64_t window_size) {
+    return guarded(h, [&] {
+        REQUIRE(window_size >= 1, "window_size must be >= 1");
+        h->window = window_size;
     });
 }
 

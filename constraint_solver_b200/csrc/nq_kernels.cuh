@@ -58,6 +58,12 @@ struct NqParams {
     long long* dump;                      // debug: every candidate delta (one chain)
     const unsigned int* skip;             // optional [chains]: 1 = leave the chain alone (ILS)
     int force_scalar;                     // v2 kernel: never take the packed path
+    // reference mode (change kind): the reference's own proposer + window + tie-break
+    int ref_mode;
+    unsigned long long window;            // .take(window_size), local_search.rs:321
+    unsigned long long* ls_rng_t;         // [chains] draw counter of the LocalSearch-owned rng
+    unsigned long long seed;
+    unsigned int chain_offset;
 };
 
 // ------------------------------------------------------------------ shared memory view
@@ -350,12 +356,65 @@ __device__ __forceinline__ void nq_scan_change(const NqSmem& s, int n, int& best
     }
 }
 
+// NQueensMoveProposer::iter_local_moves, examples/nqueens/src/lib.rs:177-205, run by one thread
+// on the chain's counters: per-column conflicts = R[r] + D1 + D2 - 3 (== get_col_scores),
+// conflicted columns in ascending order, `amount` weighted draws without replacement, then a
+// random prefix of a partial shuffle.  Same draw order as oracle/cs_oracle.c nq_ref_propose.
+// cols / sc: scratch of n entries each (u16); returns the number of chosen columns (in cols[]).
+__device__ int nq_ref_propose(const NqSmem& s, int n, PhiloxDraws& rng, uint16_t* cols,
+                              uint16_t* sc) {
+    int len = 0;
+    for (int c = 0; c < n; ++c) {
+        const int r = s.rows[c];
+        const int v = (int)s.R[r] + (int)s.D1[c - r + n - 1] + (int)s.D2[c + r] - 3;
+        if (v != 0) {
+            cols[len] = (uint16_t)c;
+            sc[len] = (uint16_t)v;
+            ++len;
+        }
+    }
+    if (len == 0) return 0;
+    int amount = n / 20;
+    amount = amount < 1 ? 1 : (amount > len ? len : amount);
+    // picked columns are compacted to the front of a second region: reuse the tail of sc[]
+    uint16_t* picked = sc + n;  // caller provides 2n entries behind sc
+    int npicked = 0;
+    for (int k = 0; k < amount; ++k) {
+        unsigned total = 0;
+        for (int q = 0; q < len; ++q) total += sc[q];
+        const unsigned x = rng.below(total);
+        unsigned acc = 0;
+        int idx = 0;
+        for (; idx < len; ++idx) {
+            acc += sc[idx];
+            if (acc > x) break;
+        }
+        picked[npicked++] = cols[idx];
+        for (int q = idx; q + 1 < len; ++q) {
+            cols[q] = cols[q + 1];
+            sc[q] = sc[q + 1];
+        }
+        --len;
+    }
+    const int num_cols = 1 + (int)rng.below((unsigned)npicked);
+    for (int k = 0; k < num_cols; ++k) {
+        const int j = k + (int)rng.below((unsigned)(npicked - k));
+        const uint16_t t = picked[k];
+        picked[k] = picked[j];
+        picked[j] = t;
+    }
+    for (int k = 0; k < num_cols; ++k) cols[k] = picked[k];
+    return num_cols;
+}
+
 // ------------------------------------------------------------------ the step kernel
 template <int TI>
 __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const NqSmem s = nq_carve(smem_raw, p.n_pad);
     const int n = p.n, tid = threadIdx.x;
+    // reference mode keeps its proposer scratch (2 x n u16) behind the regular layout
+    uint16_t* ref_scratch = (uint16_t*)(smem_raw + nq_smem_bytes(p.n_pad));
 
     for (;;) {
         __syncthreads();
@@ -394,6 +453,7 @@ __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
             }
             int v;
             unsigned int a;
+            unsigned long long ref_cand = 0;
             if (p.kind == 0) {
                 nq_compute_c(s, n);
                 __syncthreads();
@@ -404,12 +464,44 @@ __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
                     if (p.dump) nq_scan_swap<TI, false, true>(s, n, v, a, p.dump);
                     else nq_scan_swap<TI, false, false>(s, n, v, a, nullptr);
                 }
-            } else {
+            } else if (!p.ref_mode) {
                 if (p.dump) nq_scan_change<TI, true>(s, n, v, a, p.dump);
                 else nq_scan_change<TI, false>(s, n, v, a, nullptr);
+            } else {
+                // reference mode: sampled conflicted columns, window, (score, solution) order
+                __syncthreads();
+                if (tid == 0) {
+                    PhiloxDraws rng(p.seed, p.chain_offset + (unsigned)chain, 2u, p.ls_rng_t[chain]);
+                    // scratch: s.c holds the chosen columns; D-array slack is not touched:
+                    // column scores and the picked list live in the reduction-free tail of s.c
+                    s.red[97] = nq_ref_propose(s, n, rng, s.c, ref_scratch);
+                    p.ls_rng_t[chain] = rng.t;
+                }
+                __syncthreads();
+                const int ncols = s.red[97];
+                long long cand = (long long)ncols * (n - 1);
+                if ((unsigned long long)cand > p.window) cand = (long long)p.window;
+                v = NQ_INF;
+                a = 0xffffffffu;
+                for (long long q = tid; q < cand; q += blockDim.x) {
+                    const int col = s.c[q / (n - 1)];
+                    const int vv = (int)(q % (n - 1));
+                    const int r = s.rows[col];
+                    const int val = vv + (vv >= r ? 1 : 0);  // the q-th non-identity candidate
+                    const int h = nq_change_half(s, n, col, val);
+                    // derived Ord on the resulting vectors: lowering an entry beats every raise;
+                    // among lowerings the lowest column wins, among raises the highest column
+                    const unsigned key = val < r ? (unsigned)(col * n + val)
+                                                 : (unsigned)(n * n + (n - 1 - col) * n + val);
+                    if (h < v || (h == v && key < a)) {
+                        v = h;
+                        a = key;
+                    }
+                }
+                ref_cand = (unsigned long long)cand;
             }
             block_argmin(v, a, s.red);
-            scored += (unsigned long long)nbh;
+            scored += p.ref_mode ? ref_cand : (unsigned long long)nbh;
             if (p.dump) break;  // debug dump: evaluate once, accept nothing
             if (v >= NQ_INF) {  // empty neighbourhood, local_search.rs:336-338
                 status = 3;
@@ -417,7 +509,17 @@ __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
             }
             // recover b: lowest partner of row/column `a` that attains v
             unsigned int b = 0xffffffffu;
-            if (p.kind == 0) {
+            if (p.ref_mode) {  // the key encodes (column, value)
+                const unsigned nn = (unsigned)n * (unsigned)n;
+                if (a < nn) {
+                    b = a % (unsigned)n;
+                    a = a / (unsigned)n;
+                } else {
+                    const unsigned k2 = a - nn;
+                    b = k2 % (unsigned)n;
+                    a = (unsigned)(n - 1) - k2 / (unsigned)n;
+                }
+            } else if (p.kind == 0) {
                 const int ra = s.rows[a];
                 for (int j = (int)a + 1 + tid; j < n; j += blockDim.x)
                     if (s.rows[j] != ra && nq_swap_half(s, n, (int)a, j) == v) {
@@ -432,8 +534,10 @@ __global__ void __launch_bounds__(NQ_THREADS, 1) nq_step_kernel(NqParams p) {
                         break;
                     }
             }
-            int dummy = 0;
-            block_argmin(dummy, b, s.red);
+            if (!p.ref_mode) {
+                int dummy = 0;
+                block_argmin(dummy, b, s.red);
+            }
 
             const long long new_score = score + 2ll * v;
             bool improved = new_score < score;

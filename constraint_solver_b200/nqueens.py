@@ -90,7 +90,8 @@ class NQueensChains:
 
     def __init__(self, n: int, n_chains: int = 1, *, seed: int = 42, chain_offset: int = 0,
                  neighbourhood: int = SWAP, trace_capacity: int = 0, device: int = -1,
-                 force_global: bool = False, force_scalar: bool = False):
+                 force_global: bool = False, force_scalar: bool = False,
+                 reference_proposer: bool = False):
         self._lib = L.load()
         self.n, self.n_chains = int(n), int(n_chains)
         self.neighbourhood = neighbourhood
@@ -100,7 +101,8 @@ class NQueensChains:
                            trace_capacity=trace_capacity, seed=seed, device=device,
                            neighbourhood=neighbourhood,
                            flags=(L.CS_NQ_FLAG_GLOBAL if force_global else 0)
-                           | (L.CS_NQ_FLAG_SCALAR if force_scalar else 0))
+                           | (L.CS_NQ_FLAG_SCALAR if force_scalar else 0)
+                           | (L.CS_NQ_FLAG_REFERENCE_PROPOSER if reference_proposer else 0))
         h = C.c_void_p()
         rc = self._lib.cs_nq_create(C.byref(cfg), C.byref(h))
         if rc != L.CS_OK:
@@ -207,6 +209,9 @@ class NQueensChains:
         self._check(self._lib.cs_nq_neighbourhood_deltas(self._h, chain, _ptr(out), n.value, C.byref(n)),
                     "cs_nq_neighbourhood_deltas")
         return out[: n.value]
+
+    def set_window(self, window_size: int):
+        self._check(self._lib.cs_nq_set_window(self._h, window_size), "cs_nq_set_window")
 
     # -- the hot path
     @staticmethod

@@ -48,6 +48,12 @@ extern "C" {
 #define CS_NQ_MAX_N 1000000u
 #define CS_NQ_FLAG_GLOBAL 1u /* force the global-memory (big board) path for any n */
 #define CS_NQ_FLAG_SCALAR 2u /* never use the packed-window fast scan (parity / A-B testing) */
+/* Reference mode (CS_NQ_CHANGE only): the reference's own move proposer -- conflicted columns
+ * sampled by weight, a random subset of them, every row value of each
+ * (examples/nqueens/src/lib.rs:177-255) -- truncated to window_size candidates and ordered by
+ * the derived Ord (score, then solution vector), local_search.rs:315-323.  Random choices come
+ * from the chain's Philox stream CS_PHILOX_LS. */
+#define CS_NQ_FLAG_REFERENCE_PROPOSER 4u
 
 /* neighbourhood kinds */
 #define CS_NQ_SWAP 0u   /* exchange rows of columns i<j (new; defined against lib.rs:74-87) */
@@ -62,7 +68,7 @@ extern "C" {
 /* Philox stream purposes (ctr[3]) */
 #define CS_PHILOX_INIT 0u
 #define CS_PHILOX_PERTURB 1u
-#define CS_PHILOX_ACCEPT 2u
+#define CS_PHILOX_LS 2u /* the LocalSearch-owned rng (reference-mode proposer) */
 #define CS_PHILOX_HOLIDAYS 3u
 
 typedef struct cs_move {
@@ -147,6 +153,10 @@ int32_t cs_nq_enumerate(cs_nq_handle* h, uint32_t chain, cs_move* moves, uint64_
  * (c,v) row-major, n*n entries); identity -> INT64_MAX. */
 int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, int64_t* delta,
                                    uint64_t cap, uint64_t* n_out);
+
+/* window_size of LocalSearch::new (local_search.rs:281); only reference mode truncates the
+ * neighbourhood (default 5 * n, examples/nqueens/src/main.rs:130). */
+int32_t cs_nq_set_window(cs_nq_handle* h, uint64_t window_size);
 
 /* The hot path: for every chain, n_steps times: enumerate the full neighbourhood,
  * delta-score every candidate, argmin by (delta, a, b), accept unconditionally

@@ -524,6 +524,148 @@ int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
     return n_moves;
 }
 
+
+/* ------------------------------------------------------------------ reference-mode proposer */
+/* NQueensMoveProposer::iter_local_moves, examples/nqueens/src/lib.rs:177-255, followed by
+ * LocalSearch::execute's window + sort (local_search.rs:315-323), literally: candidates are
+ * full clones, each fully re-scored, ordered by the derived Ord (score, then the solution
+ * vector lexicographically).
+ * Random choices over the chain's Philox stream purpose 2 (the LocalSearch-owned rng):
+ *   choose_multiple_weighted(amount, w = score + 1e-4)  ->  `amount` sequential draws without
+ *       replacement, x = mulhi(u, sum of remaining integer scores), first column (ascending)
+ *       whose cumulative score exceeds x;
+ *   gen_range(1..=len) -> 1 + mulhi(u, len);   choose_multiple(num) -> partial Fisher-Yates
+ *       k = 0..num-1: swap(k, k + mulhi(u, len - k)).
+ * (rand 0.8.5's own sampling algorithms are un-vendored: parity unpinned at the RNG boundary.) */
+static uint32_t ls_rng_next(uint64_t seed, uint32_t chain, uint64_t* t) {
+    return orc_philox_draw(seed, chain, 2u, (*t)++);
+}
+static int64_t ls_rng_below(uint64_t seed, uint32_t chain, uint64_t* t, int64_t m) {
+    return (int64_t)(((uint64_t)ls_rng_next(seed, chain, t) * (uint64_t)m) >> 32);
+}
+
+/* returns the number of chosen columns written to `chosen` (0 = no conflicts, lib.rs:193-194) */
+static int64_t nq_ref_propose(const int64_t* rows, int64_t n, uint64_t seed, uint32_t chain,
+                              uint64_t* t, int64_t* chosen, int64_t* scratch /* 2n */) {
+    int64_t* col = scratch;
+    int64_t* sc = scratch + n;
+    orc_nq_col_scores(rows, n, sc); /* :182 */
+    int64_t len = 0;
+    for (int64_t c = 0; c < n; ++c)
+        if (sc[c] != 0) { /* :183-187, already in ascending column order (:187 sort) */
+            col[len] = c;
+            sc[len] = sc[c];
+            ++len;
+        }
+    if (len == 0) return 0;
+    int64_t amount = n / 20; /* :196 */
+    if (amount < 1) amount = 1;
+    if (amount > len) amount = len;
+    int64_t npicked = 0;
+    for (int64_t k = 0; k < amount; ++k) { /* :197-201 */
+        int64_t total = 0;
+        for (int64_t q = 0; q < len; ++q) total += sc[q];
+        const int64_t x = ls_rng_below(seed, chain, t, total);
+        int64_t acc = 0, idx = 0;
+        for (; idx < len; ++idx) {
+            acc += sc[idx];
+            if (acc > x) break;
+        }
+        chosen[npicked++] = col[idx];
+        for (int64_t q = idx; q + 1 < len; ++q) {
+            col[q] = col[q + 1];
+            sc[q] = sc[q + 1];
+        }
+        --len;
+    }
+    const int64_t num_cols = 1 + ls_rng_below(seed, chain, t, npicked); /* :202 */
+    for (int64_t k = 0; k < num_cols; ++k) {                            /* :203 */
+        const int64_t j = k + ls_rng_below(seed, chain, t, npicked - k);
+        const int64_t tmp = chosen[k];
+        chosen[k] = chosen[j];
+        chosen[j] = tmp;
+    }
+    return num_cols;
+}
+
+int64_t orc_nq_local_search_ref(int64_t* rows, int64_t n, uint64_t seed, uint32_t chain,
+                                uint64_t* rng_t, uint64_t allow_no_improvement_for,
+                                uint64_t max_iterations, uint64_t window_size, int64_t* best_score,
+                                int64_t* current_out, int64_t* trace_a, int64_t* trace_b,
+                                int64_t* trace_score, int64_t cap) {
+    const size_t bytes = sizeof(int64_t) * (size_t)(n > 0 ? n : 1);
+    int64_t* current = (int64_t*)malloc(bytes);
+    int64_t* best = (int64_t*)malloc(bytes);
+    int64_t* cand = (int64_t*)malloc(bytes);
+    int64_t* nb = (int64_t*)malloc(bytes);
+    int64_t* chosen = (int64_t*)malloc(bytes);
+    int64_t* scratch = (int64_t*)malloc(bytes * 2);
+    memcpy(current, rows, bytes);
+    int64_t current_score = orc_nq_score(current, n);
+    memcpy(best, current, bytes);
+    int64_t bscore = current_score;
+    uint64_t no_improvement_for = 0;
+    int64_t steps = 0;
+    for (uint64_t it = 0; it < max_iterations; ++it) {
+        if (current_score == 0) {
+            memcpy(best, current, bytes);
+            bscore = 0;
+            break;
+        }
+        const int64_t ncols = nq_ref_propose(current, n, seed, chain, rng_t, chosen, scratch);
+        int have = 0;
+        int64_t nb_score = 0, nb_a = -1, nb_b = -1;
+        uint64_t taken = 0;
+        for (int64_t k = 0; k < ncols && taken < window_size; ++k) { /* lib.rs:217-234 */
+            for (int64_t v = 0; v < n && taken < window_size; ++v) {
+                memcpy(cand, current, bytes);
+                cand[chosen[k]] = v;
+                if (v == current[chosen[k]]) continue; /* tabu == {current} */
+                const int64_t sc = orc_nq_score(cand, n);
+                ++taken;
+                int better;
+                if (!have) better = 1;
+                else if (sc != nb_score) better = sc < nb_score;
+                else better = lex_less(cand, nb, n); /* derived Ord: (score, solution) */
+                if (better) {
+                    have = 1;
+                    nb_score = sc;
+                    nb_a = chosen[k];
+                    nb_b = v;
+                    memcpy(nb, cand, bytes);
+                }
+            }
+        }
+        if (!have) break;
+        if (nb_score < current_score) {
+            memcpy(best, nb, bytes);
+            bscore = nb_score;
+            no_improvement_for = 0;
+        } else {
+            no_improvement_for += 1;
+            if (no_improvement_for >= allow_no_improvement_for) break;
+        }
+        memcpy(current, nb, bytes);
+        current_score = nb_score;
+        if (steps < cap) {
+            if (trace_a) trace_a[steps] = nb_a;
+            if (trace_b) trace_b[steps] = nb_b;
+            if (trace_score) trace_score[steps] = nb_score;
+        }
+        ++steps;
+    }
+    memcpy(rows, best, bytes);
+    if (best_score) *best_score = bscore;
+    if (current_out) memcpy(current_out, current, bytes);
+    free(current);
+    free(best);
+    free(cand);
+    free(nb);
+    free(chosen);
+    free(scratch);
+    return steps;
+}
+
 /* ------------------------------------------------------------------ iterated local search */
 /* IteratedLocalSearch::execute_round, local-search/src/iterated_local_search.rs:173-202, with
  *   - History::local_search_chose_solution (bounded best-set, BTreeSet ordered by
@@ -649,13 +791,21 @@ typedef struct {
     int64_t n;
     int kind;
     uint64_t allow, iters;
+    uint64_t ref_window; /* != 0: the reference's proposer + window + tie-break */
+    uint64_t seed;
+    uint32_t chain;
+    uint64_t ls_t; /* the LocalSearch-owned rng advances across execute() calls */
 } nq_ils_ctx;
 
 static int64_t nq_ils_ls(void* c, int64_t* sol) {
     nq_ils_ctx* x = (nq_ils_ctx*)c;
     int64_t best = 0;
-    orc_nq_local_search(sol, x->n, x->kind, ORC_TIE_MOVE_ORDER, x->allow, x->iters, 0, &best, NULL,
-                        NULL, NULL, NULL, NULL, 0);
+    if (x->ref_window)
+        orc_nq_local_search_ref(sol, x->n, x->seed, x->chain, &x->ls_t, x->allow, x->iters,
+                                x->ref_window, &best, NULL, NULL, NULL, NULL, 0);
+    else
+        orc_nq_local_search(sol, x->n, x->kind, ORC_TIE_MOVE_ORDER, x->allow, x->iters, 0, &best,
+                            NULL, NULL, NULL, NULL, NULL, 0);
     return best;
 }
 
@@ -675,8 +825,8 @@ static void nq_ils_restart(void* c, orc_rng* r, int64_t* sol) {
 int64_t orc_nq_ils(uint64_t seed, uint32_t chain, int64_t n, int kind, uint64_t ls_max_iterations,
                    uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
                    int64_t* best_rows, int64_t* best_score, int64_t* current_out,
-                   int64_t* round_new_score, int64_t* round_choice) {
-    nq_ils_ctx ctx = {n, kind, allow_no_improvement_for, ls_max_iterations};
+                   int64_t* round_new_score, int64_t* round_choice, uint64_t ref_window) {
+    nq_ils_ctx ctx = {n, kind, allow_no_improvement_for, ls_max_iterations, ref_window, seed, chain, 0};
     int64_t* current = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
     orc_nq_init_perm(seed, chain, n, current);
     const int64_t r = ils_core(&ctx, nq_ils_ls, nq_ils_restart, seed, chain, n, n, 0, 0, best_cap,

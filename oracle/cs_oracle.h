@@ -131,7 +131,15 @@ int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
 int64_t orc_nq_ils(uint64_t seed, uint32_t chain, int64_t n, int kind, uint64_t ls_max_iterations,
                    uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
                    int64_t* best_rows, int64_t* best_score, int64_t* current_out,
-                   int64_t* round_new_score, int64_t* round_choice);
+                   int64_t* round_new_score, int64_t* round_choice, uint64_t ref_window);
+/* LocalSearch::execute with the reference's OWN proposer (examples/nqueens/src/lib.rs:177-255:
+ * sampled conflicted columns, change moves), window (.take(window_size)) and derived-Ord
+ * tie-break (score, solution lexicographic); rng_t = LS rng draw counter (in/out). */
+int64_t orc_nq_local_search_ref(int64_t* rows, int64_t n, uint64_t seed, uint32_t chain,
+                                uint64_t* rng_t, uint64_t allow_no_improvement_for,
+                                uint64_t max_iterations, uint64_t window_size, int64_t* best_score,
+                                int64_t* current_out, int64_t* trace_a, int64_t* trace_b,
+                                int64_t* trace_score, int64_t cap);
 int64_t orc_es_ils(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
                    const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
                    const int64_t* employees, int64_t E, uint64_t ls_max_iterations,

@@ -46,6 +46,7 @@ def lib():
         _lib.orc_days_from_civil.restype = I64
         _lib.orc_philox_draw.restype = C.c_uint32
         _lib.orc_nq_ils.restype = I64
+        _lib.orc_nq_local_search_ref.restype = I64
         _lib.orc_es_ils.restype = I64
     return _lib
 
@@ -234,8 +235,29 @@ def es_baseline_sample(a, employees, x, y, kind, threads, start_weekday=0, holid
 
 
 # ---------------------------------------------------------------- iterated local search
+def nq_local_search_ref(rows, seed, chain, rng_t=0, allow_no_improvement_for=5,
+                        max_iterations=10_000, window_size=None, trace_cap=0):
+    """LocalSearch::execute with the reference's own proposer / window / tie-break."""
+    r = _i64(rows).copy()
+    n = len(r)
+    window_size = 5 * n if window_size is None else window_size
+    cur = np.zeros(max(n, 1), dtype=np.int64)
+    best_score = I64(0)
+    t = U64(rng_t)
+    ta = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    tb = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    ts = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    steps = lib().orc_nq_local_search_ref(_p(r), I64(n), U64(seed), C.c_uint32(chain), C.byref(t),
+                                          U64(allow_no_improvement_for), U64(max_iterations),
+                                          U64(window_size), C.byref(best_score), _p(cur), _p(ta),
+                                          _p(tb), _p(ts), I64(trace_cap))
+    k = min(int(steps), trace_cap)
+    return dict(best=r, best_score=int(best_score.value), current=cur[:n], steps=int(steps),
+                rng_t=int(t.value), trace_a=ta[:k], trace_b=tb[:k], trace_score=ts[:k])
+
+
 def nq_ils(seed, chain, n, kind=SWAP, ls_max_iterations=10_000, allow_no_improvement_for=5,
-           rounds=100, best_cap=32):
+           rounds=100, best_cap=32, ref_window=0):
     """IteratedLocalSearch (iterated_local_search.rs:173-202) restated; see cs_oracle.c."""
     best = np.zeros(max(n, 1), dtype=np.int64)
     cur = np.zeros(max(n, 1), dtype=np.int64)
@@ -244,7 +266,7 @@ def nq_ils(seed, chain, n, kind=SWAP, ls_max_iterations=10_000, allow_no_improve
     bs = I64(0)
     r = lib().orc_nq_ils(U64(seed), C.c_uint32(chain), I64(n), C.c_int(kind), U64(ls_max_iterations),
                          U64(allow_no_improvement_for), U64(rounds), C.c_int(best_cap), _p(best),
-                         C.byref(bs), _p(cur), _p(rn), _p(rc))
+                         C.byref(bs), _p(cur), _p(rn), _p(rc), U64(ref_window))
     r = int(r)
     return dict(rounds=r, best=best[:n], best_score=int(bs.value), current=cur[:n],
                 round_new_score=rn[:r], round_choice=rc[:r])
