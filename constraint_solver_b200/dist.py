@@ -45,7 +45,9 @@ def exchange_best(dist, local_key: torch.Tensor, rows_of, elite: torch.Tensor, r
 
 
 class BestExchange:
-    """exchange_best bound to an NQueensChains engine running on torch's current stream."""
+    """exchange_best bound to an NQueensChains or ScheduleChains engine running on torch's
+    current stream.  The packed key keeps the global chain id in its low 32 bits for both
+    problems (n-queens: score << 32; scheduling: hard << 48 | soft << 32)."""
 
     def __init__(self, eng, dist, rank: int, world: int, chains_per_rank: int):
         self.eng, self.dist, self.rank, self.world = eng, dist, rank, world
@@ -53,18 +55,19 @@ class BestExchange:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
         self.key = device_view(eng.best_key_device_ptr(), (1,), "<i8", dev)
-        self.elite = torch.zeros(eng.n, dtype=torch.int16, device=dev)
+        self.len = getattr(eng, "n", None) or eng.n_slots  # solution length (u16 elements)
+        self.elite = torch.zeros(self.len, dtype=torch.int16, device=dev)
         self.best_score = None
         self.best_chain = None
 
     def _rows_of(self, local_chain: int) -> torch.Tensor:
         ptr, _ = self.eng.chain_device_ptr(local_chain)
-        return device_view(ptr, (self.eng.n,), "<i2", self.dev)
+        return device_view(ptr, (self.len,), "<i2", self.dev)
 
     def sync(self, inject_into_worst: bool = False):
         self.best_score, self.best_chain = exchange_best(self.dist, self.key, self._rows_of,
                                                          self.elite, self.rank, self.cpr)
-        if inject_into_worst and self.best_chain // self.cpr != self.rank:
+        if inject_into_worst and self.best_chain // self.cpr != self.rank and hasattr(self.eng, "set_chain_from_device"):
             worst = int(self.eng.scores().argmax())
             self.eng.set_chain_from_device(worst, self.elite.data_ptr())
         return self.best_score, self.best_chain
