@@ -573,10 +573,21 @@ def main():
                         "are the shared-memory data pipe and the integer ALU pipe (onchip, from "
                         "the committed ncu capture; see DESIGN.md)",
                 "onchip": _onchip()}
+    # shared-memory roofline (the honest bound): bytes actually moved through the smem data pipe
+    # = wavefronts/move (committed ncu capture) x 128 B, against 128 B/clk/SM at the sampled clock
+    oc = roofline["onchip"]
+    if oc and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        smem_peak = 128.0 * sms * clocks["sm_mhz"] * 1e6 / 1e9
+        smem_ach = per_launch_moves / avg_launch_s * (oc["smem_wavefronts_per_32_moves"] / 32.0) * 128.0 / 1e9
+        roofline["smem"] = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
+                            "frac": smem_ach / smem_peak,
+                            "how": "ncu wavefronts per move x 128 B x live moves/s; peak = 128 B/clk/SM x "
+                                   f"{sms} SMs x {clocks['sm_mhz']:.0f} MHz (sampled)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"nqueens n={n}, {chains} restart chains per GPU, full swap "
                                f"neighbourhood ({n * (n - 1) // 2} candidates) delta-scored per chain-step",
                    "parallelism": f"chains sharded x{world}" if world > 1 else "1 GPU",

@@ -38,6 +38,8 @@ constexpr int ES_CBINS = 12;   // per-weekday count bins 0..11 (a weekday occurs
 constexpr int ES_TBINS = 66;   // total-days bins 0..65
 constexpr int ES_WBINS = 24;   // weekend-day bins 0..23
 constexpr long long ES_KEY_INF = 0x7fffffffffffffffll;
+constexpr int ES_KEYS = 66 * 32;  // (total days 0..65) x (weekend days 0..31)
+constexpr int ES_MAXCLS = 68;
 
 struct EsConst {
     int D, E, start_wd, n14, n7;
@@ -93,58 +95,70 @@ struct EsSmem {
     u64* eq;            // [64][4] per present-employee slot: EQ3_14, EQ4_14, EQ2_7, EQ3_7
     unsigned char* dayb;   // [5][64] per day, for its current employee: lossH, lossS1, total, weekend, weekday count
     unsigned char* pslot;  // [E] present-employee slot (0xFF = absent)
+    unsigned char* cls;    // [E] class of the employee's (total days, weekend days) pair
+    unsigned char* keymap; // [ES_KEYS] (total << 5 | weekend) -> class id
+    unsigned int* keybits; // [ES_KEYS / 32] keys in use
+    signed char* s34;      // [64][ES_MAXCLS] S3+S4 delta of giving day d to an employee of the class
+    signed char* s2t;      // [64][ES_CBINS] S2 delta of giving day d to an employee with cn days on that weekday
 };
 
-__host__ __device__ inline size_t es_smem_bytes(int D, int E) {
-    size_t b = (size_t)E * 8;                       // mask
-    b += (size_t)((D + 1 + 3) / 4 * 4) * 2;         // a (padded to 8 B)
-    b = (b + 7) / 8 * 8;
-    b += (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2;  // hist
-    b = (b + 7) / 8 * 8;
-    b += 5 * 4 + 4;                                 // occ2 + occW
-    b = (b + 7) / 8 * 8;
-    b += 8;                                         // occT
-    b += 16 * 4;                                    // misc
-    b += 40 * 8;                                    // red
-    b += 3 * 64 * 8 + 64 * 4 * 8 + 5 * 64;          // part, cont14, cont7, eq, dayb
-    b += (size_t)(E + 7) / 8 * 8;                   // pslot
-    return b;
+struct EsLayout {
+    size_t mask, a, hist, occ, occT, misc, red, day, eq, dayb, pslot, cls, keymap, keybits, s34, s2t, total;
+};
+__host__ __device__ inline size_t es_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline EsLayout es_layout(int D, int E) {
+    EsLayout L;
+    size_t o = 0;
+    L.mask = o;    o += (size_t)E * 8;
+    L.a = o;       o = es_align(o + (size_t)(D + 1) * 2, 8);
+    L.hist = o;    o = es_align(o + (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2, 8);
+    L.occ = o;     o = es_align(o + 6 * 4, 8);
+    L.occT = o;    o += 8;
+    L.misc = o;    o += 16 * 4;
+    L.red = o;     o += 40 * 8;
+    L.day = o;     o += 3 * 64 * 8;
+    L.eq = o;      o += 64 * 4 * 8;
+    L.dayb = o;    o += 5 * 64;
+    L.pslot = o;   o = es_align(o + (size_t)E, 8);
+    L.cls = o;     o = es_align(o + (size_t)E, 8);
+    L.keymap = o;  o = es_align(o + ES_KEYS, 8);
+    L.keybits = o; o = es_align(o + (ES_KEYS / 32) * 4, 8);
+    L.s34 = o;     o = es_align(o + 64 * ES_MAXCLS, 8);
+    L.s2t = o;     o = es_align(o + 64 * ES_CBINS, 8);
+    L.total = o;
+    return L;
 }
+__host__ __device__ inline size_t es_smem_bytes(int D, int E) { return es_layout(D, E).total; }
 
+// offsets only (no pointer <-> integer casts) so the compiler keeps the shared address space
 __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
+    const EsLayout L = es_layout(D, E);
     EsSmem s;
-    s.mask = (u64*)p;
-    p += (size_t)E * 8;
-    s.a = (uint16_t*)p;
-    p += (size_t)((D + 1 + 3) / 4 * 4) * 2;
-    p = (unsigned char*)(((uintptr_t)p + 7) / 8 * 8);
-    s.hist2 = (uint16_t*)p;
+    s.mask = (u64*)(p + L.mask);
+    s.a = (uint16_t*)(p + L.a);
+    s.hist2 = (uint16_t*)(p + L.hist);
     s.histT = s.hist2 + 5 * ES_CBINS;
     s.histW = s.histT + ES_TBINS;
-    p += (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2;
-    p = (unsigned char*)(((uintptr_t)p + 7) / 8 * 8);
-    s.occ2 = (unsigned int*)p;
+    s.occ2 = (unsigned int*)(p + L.occ);
     s.occW = s.occ2 + 5;
-    p += 5 * 4 + 4;
-    p = (unsigned char*)(((uintptr_t)p + 7) / 8 * 8);
-    s.occT = (u64*)p;
-    p += 8;
-    s.misc = (int*)p;
-    p += 16 * 4;
-    s.red = (u64*)p;
-    p += 40 * 8;
-    s.part = (u64*)p;
+    s.occT = (u64*)(p + L.occT);
+    s.misc = (int*)(p + L.misc);
+    s.red = (u64*)(p + L.red);
+    s.part = (u64*)(p + L.day);
     s.cont14 = s.part + 64;
     s.cont7 = s.cont14 + 64;
-    s.eq = s.cont7 + 64;
-    p += 3 * 64 * 8 + 64 * 4 * 8;
-    s.dayb = p;
-    p += 5 * 64;
-    s.pslot = p;
+    s.eq = (u64*)(p + L.eq);
+    s.dayb = p + L.dayb;
+    s.pslot = p + L.pslot;
+    s.cls = p + L.cls;
+    s.keymap = p + L.keymap;
+    s.keybits = (unsigned int*)(p + L.keybits);
+    s.s34 = (signed char*)(p + L.s34);
+    s.s2t = (signed char*)(p + L.s2t);
     return s;
 }
 
-enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10 };
+enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10, ES_NCLS = 11 };
 enum { ES_DB_LOSSH = 0, ES_DB_LOSSS = 64, ES_DB_TOT = 128, ES_DB_WK = 192, ES_DB_WD = 256 };
 
 // ------------------------------------------------------------------ per-employee terms
@@ -254,6 +268,33 @@ __device__ __forceinline__ int es_s2_delta(const EsSmem& s, int wd, int cm, int 
 
 __device__ __forceinline__ int es_weekday(const EsConst& K, int d) { return (K.start_wd + d) % 7; }
 
+// S3 + S4 delta when a day (weekend flag isw) moves from an employee with (to, wo) total /
+// weekend days to one with (tn, wn); lib.rs:345-365, min/max over PRESENT employees only.
+__device__ __forceinline__ int es_s34_change(const EsSmem& s, int to, int wo, int isw, int tn, int wn) {
+    int present = s.misc[ES_PRESENT];
+    const int oldT = es_spread(*s.occT, present), oldW = es_spread((u64)*s.occW, present);
+    EsAdj T, W;
+    T.add(to, -1);
+    W.add(wo, -1);
+    if (to - 1 >= 1) {
+        T.add(to - 1, +1);
+        W.add(wo - isw, +1);
+    } else {
+        --present;
+    }
+    if (tn >= 1) {
+        T.add(tn, -1);
+        W.add(wn, -1);
+    } else {
+        ++present;
+    }
+    T.add(tn + 1, +1);
+    W.add(wn + isw, +1);
+    const u64 occT = es_occ_after(s.histT, *s.occT, T);
+    const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
+    return es_spread(occT, present) - oldT + es_spread(occW, present) - oldW;
+}
+
 // ------------------------------------------------------------------ per-step tables
 // All sliding-window counts of one day mask at once: bit-sliced adder over the L shifted
 // copies of m; plane i bit w = bit i of popc(m & (ONES(L) << w)).
@@ -311,6 +352,49 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
         s.dayb[ES_DB_WK + d] = (unsigned char)__popcll(m & K.wkend);
         s.dayb[ES_DB_WD + d] = (unsigned char)(wd < 5 ? __popcll(m & K.wd[wd]) : 0);
     }
+    // classes of (total days, weekend days): the soft S3+S4 delta of a change move depends on
+    // the receiving employee only through this pair, so it is tabulated per (day, class)
+    for (int k = tid; k < ES_KEYS / 32; k += nt) s.keybits[k] = 0;
+    __syncthreads();
+    for (int e = tid; e < K.E; e += nt) {
+        const u64 m = s.mask[e];
+        const int key = (__popcll(m) << 5) | __popcll(m & K.wkend);
+        atomicOr(&s.keybits[key >> 5], 1u << (key & 31));
+    }
+    __syncthreads();
+    if (tid == 0) {  // deterministic class ids in ascending key order
+        int nc = 0;
+        for (int w = 0; w < ES_KEYS / 32; ++w) {
+            unsigned bits = s.keybits[w];
+            while (bits) {
+                const int b = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+                s.keymap[w * 32 + b] = (unsigned char)nc;
+                ((unsigned short*)s.red)[nc] = (unsigned short)(w * 32 + b);  // class -> key
+                ++nc;
+            }
+        }
+        s.misc[ES_NCLS] = nc;
+    }
+    __syncthreads();
+    const int ncls = s.misc[ES_NCLS];
+    for (int e = tid; e < K.E; e += nt) {
+        const u64 m = s.mask[e];
+        s.cls[e] = s.keymap[(__popcll(m) << 5) | __popcll(m & K.wkend)];
+    }
+    for (int k = tid; k < K.D * ncls; k += nt) {
+        const int d = k / ncls, c = k - d * ncls;
+        const int key = ((const unsigned short*)s.red)[c];
+        const int isw = (K.wkend >> d) & 1ull ? 1 : 0;
+        s.s34[d * ES_MAXCLS + c] = (signed char)es_s34_change(
+            s, s.dayb[ES_DB_TOT + d], s.dayb[ES_DB_WK + d], isw, key >> 5, key & 31);
+    }
+    for (int k = tid; k < K.D * ES_CBINS; k += nt) {
+        const int d = k / ES_CBINS, cn = k - d * ES_CBINS;
+        const int wd = (K.start_wd + d) % 7;
+        s.s2t[k] = (signed char)((wd < 5 && cn < ES_CBINS - 1)
+                                     ? es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], cn) : 0);
+    }
     __syncthreads();
 }
 
@@ -319,46 +403,19 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
 __device__ __forceinline__ void es_change_delta(const EsSmem& s, const EsConst& K,
                                                 const u64* __restrict__ hol, int d, int en,
                                                 int& dh, int& ds) {
-    const u64 bit = 1ull << d;
     const u64 mn = s.mask[en];
     dh = (int)((hol[en] >> d) & 1ull) - (int)s.dayb[ES_DB_LOSSH + d];
     ds = -(int)s.dayb[ES_DB_LOSSS + d];
-    int tn = 0, wn = 0, cn = 0;
+    int cn = 0;
     const int wd = es_weekday(K, d);
     if (mn) {  // an absent employee has no pairs and no window counts
         const u64* q = s.eq + (int)s.pslot[en] * 4;
         dh += __popcll(mn & s.part[d]) + __popcll(q[0] & s.cont14[d]);
         ds += __popcll(q[2] & s.cont7[d]);
-        tn = __popcll(mn);
-        wn = __popcll(mn & K.wkend);
         if (wd < 5) cn = __popcll(mn & K.wd[wd]);
     }
-    if (wd < 5) ds += es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], cn);
-    // S3 / S4 over present employees
-    const int to = s.dayb[ES_DB_TOT + d], wo = s.dayb[ES_DB_WK + d];
-    const int isw = (K.wkend & bit) ? 1 : 0;
-    int present = s.misc[ES_PRESENT];
-    const int oldT = es_spread(*s.occT, present), oldW = es_spread((u64)*s.occW, present);
-    EsAdj T, W;
-    T.add(to, -1);
-    W.add(wo, -1);
-    if (to - 1 >= 1) {
-        T.add(to - 1, +1);
-        W.add(wo - isw, +1);
-    } else {
-        --present;
-    }
-    if (tn >= 1) {
-        T.add(tn, -1);
-        W.add(wn, -1);
-    } else {
-        ++present;
-    }
-    T.add(tn + 1, +1);
-    W.add(wn + isw, +1);
-    const u64 occT = es_occ_after(s.histT, *s.occT, T);
-    const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
-    ds += es_spread(occT, present) - oldT + es_spread(occW, present) - oldW;
+    // S2 / S3+S4: memoised per (day, weekday count) and per (day, (total, weekend) class)
+    ds += (int)s.s2t[d * ES_CBINS + cn] + (int)s.s34[d * ES_MAXCLS + (int)s.cls[en]];
 }
 
 // swap: days d1 < d2 exchange employees (different).
