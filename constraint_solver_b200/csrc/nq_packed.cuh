@@ -27,7 +27,10 @@
 
 namespace csb {
 
-constexpr int NQC_TI = 8;          // column slots per warp tile (two 4-byte windows)
+#ifndef NQC_TI_VALUE
+#define NQC_TI_VALUE 16
+#endif
+constexpr int NQC_TI = NQC_TI_VALUE;  // column slots per warp tile (TI/4 four-byte windows)
 constexpr int NQC_TJ = 4;          // columns per lane
 constexpr int NQC_CHUNK = 32 * NQC_TJ;
 constexpr int NQC_MAX_COUNT = 62;  // 4 counters + slack stay below 256
@@ -175,7 +178,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
     for (int k = 0; k * W < num_tiles; ++k) {
         const int t = k * W + ((k & 1) ? (W - 1 - w) : w);
         if (t >= num_tiles) continue;
-        const int i0 = t * TI;  // multiple of 8
+        const int i0 = t * TI;  // multiple of TI (>= 8, so the copy select is tile-invariant)
         const int jbase = i0 & ~(NQC_CHUNK - 1);  // first chunk (holds the tile); the loop
                                                   // offset dj below is warp-uniform by construction
         // per-slot lane-consecutive read offsets (copy fixed by the slot's row, word = 4*lane)
@@ -213,10 +216,10 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
 #pragma unroll
             for (int a = 0; a < TI; ++a)
                 T[a] = *(const unsigned*)(smem0 + pv1[a] + dj) + *(const unsigned*)(smem0 + pv2[a] + dj);
-            // transpose bytes: TP[b][0] = slots 0..3 at j_b, TP[b][1] = slots 4..7 at j_b
-            unsigned TP[NQC_TJ][2];
+            // transpose bytes: TP[b][g] = slots 4g..4g+3 at j_b
+            unsigned TP[NQC_TJ][TI / 4];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < TI / 4; ++g) {
                 const unsigned x0 = __byte_perm(T[4 * g + 0], T[4 * g + 1], 0x5140);
                 const unsigned x1 = __byte_perm(T[4 * g + 2], T[4 * g + 3], 0x5140);
                 const unsigned y0 = __byte_perm(T[4 * g + 0], T[4 * g + 1], 0x7362);
@@ -235,8 +238,10 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 const int t1 = A1 - rj, t2 = A2 + rj;
                 const unsigned char* g1 = smem0 + t1 + (t1 & 3) * ldbm1;
                 const unsigned char* g2 = smem0 + q2off + t2 + (t2 & 3) * ldbm1;
-                const unsigned Xlo = *(const unsigned*)g1 + *(const unsigned*)g2 + TP[b][0];
-                const unsigned Xhi = *(const unsigned*)(g1 + 4) + *(const unsigned*)(g2 + 4) + TP[b][1];
+                unsigned X[TI / 4];
+#pragma unroll
+                for (int g = 0; g < TI / 4; ++g)
+                    X[g] = *(const unsigned*)(g1 + 4 * g) + *(const unsigned*)(g2 + 4 * g) + TP[b][g];
                 // bcast16 takes the low 16 bits; kj is biased by NQC_BIAS so both halves stay
                 // positive and the packed add below is a plain 32-bit add (no inter-half carry)
                 // positive 16-bit values broadcast to both halves by a multiply (FMA pipe, no PRMT)
@@ -245,8 +250,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
                 const unsigned wb = (unsigned)(2 * (rj + j)) * 0x10001u;
 #pragma unroll
                 for (int p = 0; p < TI / 2; ++p) {
-                    const unsigned src = (p < 2) ? Xlo : Xhi;
-                    const unsigned x16 = __byte_perm(src, 0u, (p & 1) ? 0x4342 : 0x4140);
+                    const unsigned x16 = __byte_perm(X[p / 2], 0u, (p & 1) ? 0x4342 : 0x4140);
                     unsigned y = x16 + kj;
                     // att: equal diagonal ids -> XNOR = 0xFFFF (= -1), else <= 0xFFFD (= -3)
                     const unsigned a2 = __vimax3_u16x2(ub ^ NU[p], wb ^ NW[p], 0xFFFDFFFDu);
