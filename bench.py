@@ -611,7 +611,7 @@ def main():
 
 def _onchip():
     """shared-memory / ALU pipe utilisation of the dominant kernel from the committed capture"""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_full_nq_step_kernel_v2.json")
+    p = os.path.join(ROOT, "profiles", "r1_ncu_full_nq_step_kernel_v2_16slot.json")
     try:
         d = json.load(open(p))
         f = lambda k: float(d[k].split()[0])
@@ -619,7 +619,7 @@ def _onchip():
                 "alu_pipe_pct_of_peak": f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                 "sm_throughput_pct": f("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
                 "smem_wavefronts_per_32_moves": d["derived"]["wavefronts_per_32_moves"],
-                "source": "profiles/r1_ncu_full_nq_step_kernel_v2.json (296-chain capture)"}
+                "source": "profiles/r1_ncu_full_nq_step_kernel_v2_16slot.json (296-chain capture)"}
     except Exception:
         return None
 
