@@ -77,7 +77,7 @@ struct EsParams {
     const unsigned int* skip;  // optional [chains]: 1 = leave the chain alone (ILS)
 };
 
-// per-chain shared state
+// per-chain shared state.  NS = min(E, D) bounds the number of PRESENT employees ("slots").
 struct EsSmem {
     u64* mask;          // [E]
     uint16_t* a;        // [stride]
@@ -87,45 +87,62 @@ struct EsSmem {
     unsigned int* occ2; // [5]  bit c: some employee has exactly c days on that weekday (c>=1)
     u64* occT;          // [1]  bit c: some employee has exactly c days in total (c>=1)
     unsigned int* occW; // [1]  bit c: some PRESENT employee has exactly c weekend days (c>=0)
+    u64* fmask;         // [1]  bit d: day d is the FIRST day of its employee (one bit per present employee)
     int* misc;          // [16] present, distinct[5], hard, soft, ...
     u64* red;           // [40] reduction scratch
     u64* part;          // [64] H2/H3 partner-day mask per day
     u64* cont14;        // [64] 14-day window starts whose window contains the day
     u64* cont7;         // [64]
-    u64* eq;            // [64][4] per present-employee slot: EQ3_14, EQ4_14, EQ2_7, EQ3_7
-    unsigned char* dayb;   // [5][64] per day, for its current employee: lossH, lossS1, total, weekend, weekday count
-    unsigned char* pslot;  // [E] present-employee slot (0xFF = absent)
-    unsigned char* cls;    // [E] class of the employee's (total days, weekend days) pair
-    unsigned char* keymap; // [ES_KEYS] (total << 5 | weekend) -> class id
-    unsigned int* keybits; // [ES_KEYS / 32] keys in use
-    signed char* s34;      // [64][ES_MAXCLS] S3+S4 delta of giving day d to an employee of the class
+    u64* wdm;           // [64] days on the same weekday as d (0 for weekend days)
+    u64* eq;            // [NS][4] per slot: EQ3_14, EQ4_14, EQ2_7, EQ3_7 ("count == k" window starts)
+    u64* smask;         // [NS] day mask of the slot's employee
+    u64* shol;          // [NS] its holiday mask
+    uint16_t* semp;     // [NS] its employee index
+    uint16_t* skey;     // [NS+1] (total days << 5 | weekend days); [nslot] = 0 = an absent employee
+    unsigned char* srep;   // [NS+1] lowest column with the same key (S3+S4 class representative)
+    unsigned char* dslot;  // [64] slot of the day's current employee
+    unsigned char* dayb;   // [3][64] per day, for its current employee: total, weekend, weekday count
+    unsigned int* base;    // [64] packed (0x8000 - lossH) << 16 | (0x8000 - lossS1) of the day's employee
+    unsigned int* baseAbs; // [64] packed value of giving day d to an absent employee without a holiday
+    signed char* s34;      // [64][ls34] S3+S4 delta of giving day d to an employee of column's class
     signed char* s2t;      // [64][ES_CBINS] S2 delta of giving day d to an employee with cn days on that weekday
+    int ns, ls34;
 };
 
 struct EsLayout {
-    size_t mask, a, hist, occ, occT, misc, red, day, eq, dayb, pslot, cls, keymap, keybits, s34, s2t, total;
+    size_t mask, a, hist, occ, occT, fmask, misc, red, day, eq, smask, shol, semp, skey, srep, dslot, dayb, base,
+        baseAbs, s34, s2t, total;
+    int ns, ls34;
 };
 __host__ __device__ inline size_t es_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline EsLayout es_layout(int D, int E) {
     EsLayout L;
+    L.ns = E < D ? E : D;
+    if (L.ns < 1) L.ns = 1;
+    L.ls34 = (L.ns + 1 + 3) & ~3;
     size_t o = 0;
     L.mask = o;    o += (size_t)E * 8;
-    L.a = o;       o = es_align(o + (size_t)(D + 1) * 2, 8);
-    L.hist = o;    o = es_align(o + (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2, 8);
-    L.occ = o;     o = es_align(o + 6 * 4, 8);
     L.occT = o;    o += 8;
-    L.misc = o;    o += 16 * 4;
+    L.fmask = o;   o += 8;
     L.red = o;     o += 40 * 8;
-    L.day = o;     o += 3 * 64 * 8;
-    L.eq = o;      o += 64 * 4 * 8;
-    L.dayb = o;    o += 5 * 64;
-    L.pslot = o;   o = es_align(o + (size_t)E, 8);
-    L.cls = o;     o = es_align(o + (size_t)E, 8);
-    L.keymap = o;  o = es_align(o + ES_KEYS, 8);
-    L.keybits = o; o = es_align(o + (ES_KEYS / 32) * 4, 8);
-    L.s34 = o;     o = es_align(o + 64 * ES_MAXCLS, 8);
+    L.day = o;     o += 4 * 64 * 8;
+    L.eq = o;      o += (size_t)L.ns * 4 * 8;
+    L.smask = o;   o += (size_t)L.ns * 8;
+    L.shol = o;    o += (size_t)L.ns * 8;
+    L.misc = o;    o += 16 * 4;
+    L.occ = o;     o = es_align(o + 6 * 4, 8);
+    L.base = o;    o += 64 * 4;
+    L.baseAbs = o; o += 64 * 4;
+    L.hist = o;    o = es_align(o + (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2, 8);
+    L.a = o;       o = es_align(o + (size_t)(D + 1) * 2, 8);
+    L.semp = o;    o = es_align(o + (size_t)L.ns * 2, 8);
+    L.skey = o;    o = es_align(o + (size_t)(L.ns + 1) * 2, 8);
+    L.srep = o;    o = es_align(o + (size_t)(L.ns + 1), 8);
+    L.dslot = o;   o += 64;
+    L.dayb = o;    o += 3 * 64;
+    L.s34 = o;     o = es_align(o + (size_t)64 * L.ls34, 8);
     L.s2t = o;     o = es_align(o + 64 * ES_CBINS, 8);
-    L.total = o;
+    L.total = es_align(o, 16);
     return L;
 }
 __host__ __device__ inline size_t es_smem_bytes(int D, int E) { return es_layout(D, E).total; }
@@ -134,6 +151,8 @@ __host__ __device__ inline size_t es_smem_bytes(int D, int E) { return es_layout
 __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     const EsLayout L = es_layout(D, E);
     EsSmem s;
+    s.ns = L.ns;
+    s.ls34 = L.ls34;
     s.mask = (u64*)(p + L.mask);
     s.a = (uint16_t*)(p + L.a);
     s.hist2 = (uint16_t*)(p + L.hist);
@@ -142,24 +161,30 @@ __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     s.occ2 = (unsigned int*)(p + L.occ);
     s.occW = s.occ2 + 5;
     s.occT = (u64*)(p + L.occT);
+    s.fmask = (u64*)(p + L.fmask);
     s.misc = (int*)(p + L.misc);
     s.red = (u64*)(p + L.red);
     s.part = (u64*)(p + L.day);
     s.cont14 = s.part + 64;
     s.cont7 = s.cont14 + 64;
+    s.wdm = s.cont7 + 64;
     s.eq = (u64*)(p + L.eq);
+    s.smask = (u64*)(p + L.smask);
+    s.shol = (u64*)(p + L.shol);
+    s.semp = (uint16_t*)(p + L.semp);
+    s.skey = (uint16_t*)(p + L.skey);
+    s.srep = p + L.srep;
+    s.dslot = p + L.dslot;
     s.dayb = p + L.dayb;
-    s.pslot = p + L.pslot;
-    s.cls = p + L.cls;
-    s.keymap = p + L.keymap;
-    s.keybits = (unsigned int*)(p + L.keybits);
+    s.base = (unsigned int*)(p + L.base);
+    s.baseAbs = (unsigned int*)(p + L.baseAbs);
     s.s34 = (signed char*)(p + L.s34);
     s.s2t = (signed char*)(p + L.s2t);
     return s;
 }
 
-enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10, ES_NCLS = 11 };
-enum { ES_DB_LOSSH = 0, ES_DB_LOSSS = 64, ES_DB_TOT = 128, ES_DB_WK = 192, ES_DB_WD = 256 };
+enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10, ES_SAME = 11 };
+enum { ES_DB_TOT = 0, ES_DB_WK = 64, ES_DB_WD = 128 };
 
 // ------------------------------------------------------------------ per-employee terms
 __device__ __forceinline__ int es_pair_terms(u64 m, u64 hol, const EsConst& K) {
@@ -179,30 +204,6 @@ __device__ __forceinline__ int es_win_viol(u64 m, u64 W, int lo, int hi, int thr
 __device__ __forceinline__ void es_emp_full(u64 m, u64 hol, const EsConst& K, int& hard, int& s1) {
     hard = es_pair_terms(m, hol, K) + es_win_viol(m, 0x3fffull, 0, K.n14 - 1, 3);
     s1 = es_win_viol(m, 0x7full, 0, K.n7 - 1, 2);
-}
-
-// delta of (hard, S1) when an employee's mask changes m -> m2
-__device__ __forceinline__ void es_emp_delta(u64 m, u64 m2, u64 hol, const EsConst& K, int& dh,
-                                             int& ds) {
-    dh += es_pair_terms(m2, hol, K) - es_pair_terms(m, hol, K);
-    const u64 x = m ^ m2;
-    const int lo_d = __ffsll((long long)x) - 1, hi_d = 63 - __clzll((long long)x);
-    {   // 14-day windows touching a changed day
-        const int lo = max(0, lo_d - 13), hi = min(K.n14 - 1, hi_d);
-        for (int w = lo; w <= hi; ++w) {
-            const u64 W = 0x3fffull << w;
-            if (!(W & x)) continue;
-            dh += (__popcll(m2 & W) > 3) - (__popcll(m & W) > 3);
-        }
-    }
-    {   // 7-day windows
-        const int lo = max(0, lo_d - 6), hi = min(K.n7 - 1, hi_d);
-        for (int w = lo; w <= hi; ++w) {
-            const u64 W = 0x7full << w;
-            if (!(W & x)) continue;
-            ds += (__popcll(m2 & W) > 2) - (__popcll(m & W) > 2);
-        }
-    }
 }
 
 // ------------------------------------------------------------------ histogram helpers
@@ -295,7 +296,7 @@ __device__ __forceinline__ int es_s34_change(const EsSmem& s, int to, int wo, in
     return es_spread(occT, present) - oldT + es_spread(occW, present) - oldW;
 }
 
-// ------------------------------------------------------------------ per-step tables
+// ------------------------------------------------------------------ tallies and per-step tables
 // All sliding-window counts of one day mask at once: bit-sliced adder over the L shifted
 // copies of m; plane i bit w = bit i of popc(m & (ONES(L) << w)).
 template <int L, int PLANES>
@@ -314,202 +315,69 @@ __device__ __forceinline__ void es_window_planes(u64 m, u64 (&pl)[PLANES]) {
     }
 }
 
-// Once per chain-step (masks must be current): present-employee slots, their "count == k"
-// window masks, and the per-day tables of the day's current employee.  Block-cooperative.
-__device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol) {
+__device__ __forceinline__ void es_hist16_inc(uint16_t* hist2, int idx) {  // 16-bit bin through its 32-bit word
+    atomicAdd((unsigned int*)hist2 + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
+}
+
+// slot of a present employee = rank of its first day among the first days
+__device__ __forceinline__ int es_slot_of(const EsSmem& s, u64 m) {
+    const int f = __ffsll((long long)m) - 1;
+    return __popcll(*s.fmask & ((1ull << f) - 1ull));
+}
+
+// Tallies from the day masks (must be current): count histograms, occupancy sets, present /
+// distinct counters, the first-day mask.  Work is per DAY (<= 64 threads busy), never per
+// employee.  SCORE additionally accumulates the full (hard, S1) into misc[ES_HARD/ES_SOFT].
+template <bool SCORE>
+__device__ void es_tally(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) s.misc[ES_NSLOT] = 0;
-    __syncthreads();
-    const u64 v14 = K.n14 >= 64 ? ~0ull : ((1ull << K.n14) - 1);  // real window starts only
-    const u64 v7 = K.n7 >= 64 ? ~0ull : ((1ull << K.n7) - 1);
-    for (int e = tid; e < K.E; e += nt) {
-        const u64 m = s.mask[e];
-        if (!m) {
-            s.pslot[e] = 0xFF;
-            continue;
-        }
-        const int slot = atomicAdd(&s.misc[ES_NSLOT], 1);
-        s.pslot[e] = (unsigned char)slot;
-        u64 p14[4], p7[3];
-        es_window_planes<14, 4>(m, p14);
-        es_window_planes<7, 3>(m, p7);
-        u64* q = s.eq + slot * 4;
-        q[0] = p14[0] & p14[1] & ~p14[2] & ~p14[3] & v14;   // count == 3 (one more => H4 violation)
-        q[1] = ~p14[0] & ~p14[1] & p14[2] & ~p14[3] & v14;  // count == 4 (one less => violation gone)
-        q[2] = ~p7[0] & p7[1] & ~p7[2] & v7;                // count == 2
-        q[3] = p7[0] & p7[1] & ~p7[2] & v7;                 // count == 3
+    for (int k = tid; k < (5 * ES_CBINS + ES_TBINS + ES_WBINS) / 2; k += nt) ((unsigned int*)s.hist2)[k] = 0;
+    if (tid < 6) s.occ2[tid] = 0;  // occ2[0..4] and occW
+    if (tid < 16 && tid != ES_BCAST && tid != ES_BCAST + 1) s.misc[tid] = 0;
+    if (tid == 0) {
+        *s.occT = 0;
+        *s.fmask = 0;
     }
     __syncthreads();
     for (int d = tid; d < K.D; d += nt) {
-        const int eo = s.a[d];
-        const u64 m = s.mask[eo];
-        const u64* q = s.eq + (int)s.pslot[eo] * 4;
-        const int wd = (K.start_wd + d) % 7;
-        s.dayb[ES_DB_LOSSH + d] = (unsigned char)(((hol[eo] >> d) & 1ull) + __popcll(m & s.part[d]) +
-                                                  __popcll(q[1] & s.cont14[d]));
-        s.dayb[ES_DB_LOSSS + d] = (unsigned char)__popcll(q[3] & s.cont7[d]);
-        s.dayb[ES_DB_TOT + d] = (unsigned char)__popcll(m);
-        s.dayb[ES_DB_WK + d] = (unsigned char)__popcll(m & K.wkend);
-        s.dayb[ES_DB_WD + d] = (unsigned char)(wd < 5 ? __popcll(m & K.wd[wd]) : 0);
-    }
-    // classes of (total days, weekend days): the soft S3+S4 delta of a change move depends on
-    // the receiving employee only through this pair, so it is tabulated per (day, class)
-    for (int k = tid; k < ES_KEYS / 32; k += nt) s.keybits[k] = 0;
-    __syncthreads();
-    for (int e = tid; e < K.E; e += nt) {
+        const int e = s.a[d];
         const u64 m = s.mask[e];
-        const int key = (__popcll(m) << 5) | __popcll(m & K.wkend);
-        atomicOr(&s.keybits[key >> 5], 1u << (key & 31));
-    }
-    __syncthreads();
-    if (tid == 0) {  // deterministic class ids in ascending key order
-        int nc = 0;
-        for (int w = 0; w < ES_KEYS / 32; ++w) {
-            unsigned bits = s.keybits[w];
-            while (bits) {
-                const int b = __ffs((int)bits) - 1;
-                bits &= bits - 1;
-                s.keymap[w * 32 + b] = (unsigned char)nc;
-                ((unsigned short*)s.red)[nc] = (unsigned short)(w * 32 + b);  // class -> key
-                ++nc;
-            }
+        if (m & ((1ull << d) - 1ull)) continue;  // not the employee's first day
+        atomicOr(s.fmask, 1ull << d);
+        const int t = __popcll(m), w = __popcll(m & K.wkend);
+        es_hist16_inc(s.hist2, (int)(s.histT - s.hist2) + t);
+        es_hist16_inc(s.hist2, (int)(s.histW - s.hist2) + w);
+        atomicOr(s.occT, 1ull << t);
+        atomicOr(s.occW, 1u << w);
+        atomicAdd(&s.misc[ES_PRESENT], 1);
+        atomicAdd(&s.misc[ES_SAME], t * (t - 1) / 2);  // day pairs held by one employee (identity swaps)
+#pragma unroll
+        for (int wd = 0; wd < 5; ++wd) {
+            const int c = __popcll(m & K.wd[wd]);
+            if (!c) continue;
+            es_hist16_inc(s.hist2, wd * ES_CBINS + c);
+            atomicOr(&s.occ2[wd], 1u << c);
+            atomicAdd(&s.misc[ES_DISTINCT0 + wd], 1);
         }
-        s.misc[ES_NCLS] = nc;
-    }
-    __syncthreads();
-    const int ncls = s.misc[ES_NCLS];
-    for (int e = tid; e < K.E; e += nt) {
-        const u64 m = s.mask[e];
-        s.cls[e] = s.keymap[(__popcll(m) << 5) | __popcll(m & K.wkend)];
-    }
-    for (int k = tid; k < K.D * ncls; k += nt) {
-        const int d = k / ncls, c = k - d * ncls;
-        const int key = ((const unsigned short*)s.red)[c];
-        const int isw = (K.wkend >> d) & 1ull ? 1 : 0;
-        s.s34[d * ES_MAXCLS + c] = (signed char)es_s34_change(
-            s, s.dayb[ES_DB_TOT + d], s.dayb[ES_DB_WK + d], isw, key >> 5, key & 31);
-    }
-    for (int k = tid; k < K.D * ES_CBINS; k += nt) {
-        const int d = k / ES_CBINS, cn = k - d * ES_CBINS;
-        const int wd = (K.start_wd + d) % 7;
-        s.s2t[k] = (signed char)((wd < 5 && cn < ES_CBINS - 1)
-                                     ? es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], cn) : 0);
+        if (SCORE) {
+            int eh, es;
+            es_emp_full(m, hol[e], K, eh, es);
+            atomicAdd(&s.misc[ES_HARD], eh);
+            atomicAdd(&s.misc[ES_SOFT], es);
+        }
     }
     __syncthreads();
 }
 
-// ------------------------------------------------------------------ move deltas
-// change: day d gets employee en (!= current).  Returns (dhard, dsoft).
-__device__ __forceinline__ void es_change_delta(const EsSmem& s, const EsConst& K,
-                                                const u64* __restrict__ hol, int d, int en,
-                                                int& dh, int& ds) {
-    const u64 mn = s.mask[en];
-    dh = (int)((hol[en] >> d) & 1ull) - (int)s.dayb[ES_DB_LOSSH + d];
-    ds = -(int)s.dayb[ES_DB_LOSSS + d];
-    int cn = 0;
-    const int wd = es_weekday(K, d);
-    if (mn) {  // an absent employee has no pairs and no window counts
-        const u64* q = s.eq + (int)s.pslot[en] * 4;
-        dh += __popcll(mn & s.part[d]) + __popcll(q[0] & s.cont14[d]);
-        ds += __popcll(q[2] & s.cont7[d]);
-        if (wd < 5) cn = __popcll(mn & K.wd[wd]);
-    }
-    // S2 / S3+S4: memoised per (day, weekday count) and per (day, (total, weekend) class)
-    ds += (int)s.s2t[d * ES_CBINS + cn] + (int)s.s34[d * ES_MAXCLS + (int)s.cls[en]];
-}
-
-// swap: days d1 < d2 exchange employees (different).
-__device__ __forceinline__ void es_swap_delta(const EsSmem& s, const EsConst& K,
-                                              const u64* __restrict__ hol, int d1, int d2, int& dh,
-                                              int& ds) {
-    const int e1 = s.a[d1], e2 = s.a[d2];
-    const u64 b1 = 1ull << d1, b2 = 1ull << d2;
-    const u64 m1 = s.mask[e1], m2 = s.mask[e2];
-    const u64* q1 = s.eq + (int)s.pslot[e1] * 4;
-    const u64* q2 = s.eq + (int)s.pslot[e2] * 4;
-    const u64 h1 = hol[e1], h2 = hol[e2];
-    // windows holding exactly one of the two days change count by one for each employee
-    const u64 c14a = s.cont14[d1], c14b = s.cont14[d2], c7a = s.cont7[d1], c7b = s.cont7[d2];
-    const u64 only14a = c14a & ~c14b, only14b = c14b & ~c14a, only7a = c7a & ~c7b, only7b = c7b & ~c7a;
-    dh = (int)((h1 >> d2) & 1ull) - (int)((h1 >> d1) & 1ull) + (int)((h2 >> d1) & 1ull) -
-         (int)((h2 >> d2) & 1ull);
-    // H2/H3 pairs: e1 leaves d1 and lands on d2 (its other days: m1 without d1), e2 the reverse
-    dh += __popcll((m1 & ~b1) & s.part[d2]) - __popcll(m1 & s.part[d1]);
-    dh += __popcll((m2 & ~b2) & s.part[d1]) - __popcll(m2 & s.part[d2]);
-    // H4: e1 loses a day in windows with only d1 (count 4 -> 3), gains in windows with only d2
-    dh += __popcll(q1[0] & only14b) - __popcll(q1[1] & only14a);
-    dh += __popcll(q2[0] & only14a) - __popcll(q2[1] & only14b);
-    ds = __popcll(q1[2] & only7b) - __popcll(q1[3] & only7a);
-    ds += __popcll(q2[2] & only7a) - __popcll(q2[3] & only7b);
-    const int wd1 = es_weekday(K, d1), wd2 = es_weekday(K, d2);
-    if (wd1 != wd2) {
-        // the two weekdays are distinct histograms, so their deltas are independent
-        if (wd1 < 5)
-            ds += es_s2_delta(s, wd1, __popcll(m1 & K.wd[wd1]), __popcll(m2 & K.wd[wd1]));
-        if (wd2 < 5)
-            ds += es_s2_delta(s, wd2, __popcll(m2 & K.wd[wd2]), __popcll(m1 & K.wd[wd2]));
-    }
-    const int k1 = (K.wkend & b1) ? 1 : 0, k2 = (K.wkend & b2) ? 1 : 0;
-    if (k1 != k2) {  // totals (S3) unchanged; weekend counts move between the two employees
-        const int present = s.misc[ES_PRESENT];
-        const int w1 = __popcll(m1 & K.wkend), w2 = __popcll(m2 & K.wkend);
-        EsAdj W;
-        W.add(w1, -1);
-        W.add(w1 - k1 + k2, +1);
-        W.add(w2, -1);
-        W.add(w2 + k1 - k2, +1);
-        const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
-        ds += es_spread(occW, present) - es_spread((u64)*s.occW, present);
-    }
-}
-
-// ------------------------------------------------------------------ tallies (K4)
-// Build masks + histograms from a[] and the full score from them.  Block-cooperative.
+// Build masks + tallies from a[] and the full score from them.  Block-cooperative.
 __device__ void es_build(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol,
                          int& hard, int& soft) {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int e = tid; e < K.E; e += nt) s.mask[e] = 0;
-    for (int k = tid; k < 5 * ES_CBINS + ES_TBINS + ES_WBINS; k += nt) s.hist2[k] = 0;
-    if (tid < 5) s.occ2[tid] = 0;
-    if (tid < 16) s.misc[tid] = 0;
-    if (tid == 0) {
-        *s.occT = 0;
-        *s.occW = 0;
-    }
     __syncthreads();
     for (int d = tid; d < K.D; d += nt) atomicOr(&s.mask[s.a[d]], 1ull << d);
     __syncthreads();
-    int h = 0, s1 = 0;
-    for (int e = tid; e < K.E; e += nt) {
-        const u64 m = s.mask[e];
-        if (!m) continue;
-        int eh, es;
-        es_emp_full(m, hol[e], K, eh, es);
-        h += eh;
-        s1 += es;
-        atomicAdd(&s.misc[ES_PRESENT], 1);
-        const int t = __popcll(m), w = __popcll(m & K.wkend);
-        // 16-bit histogram bins: add through the containing 32-bit word
-        {
-            const int idx = (int)(s.histT - s.hist2) + t;
-            atomicAdd((unsigned int*)s.hist2 + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
-            const int idw = (int)(s.histW - s.hist2) + w;
-            atomicAdd((unsigned int*)s.hist2 + (idw >> 1), (idw & 1) ? 0x10000u : 1u);
-        }
-        atomicOr(s.occT, 1ull << t);
-        atomicOr(s.occW, 1u << w);
-        for (int wd = 0; wd < 5; ++wd) {
-            const int c = __popcll(m & K.wd[wd]);
-            if (!c) continue;
-            const int idx = wd * ES_CBINS + c;
-            atomicAdd((unsigned int*)s.hist2 + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
-            atomicOr(&s.occ2[wd], 1u << c);
-            atomicAdd(&s.misc[ES_DISTINCT0 + wd], 1);
-        }
-    }
-    atomicAdd(&s.misc[ES_HARD], h);
-    atomicAdd(&s.misc[ES_SOFT], s1);
-    __syncthreads();
+    es_tally<true>(s, K, hol);
     hard = s.misc[ES_HARD];
     soft = s.misc[ES_SOFT];
     const int present = s.misc[ES_PRESENT];
@@ -518,49 +386,175 @@ __device__ void es_build(const EsSmem& s, const EsConst& K, const u64* __restric
     __syncthreads();
 }
 
-// single-thread application of an accepted move to the tallies
-__device__ void es_hist_move(uint16_t* hist, unsigned int* occ32, u64* occ64, int from, int to) {
-    // from/to < 0 : no such side
-    if (from >= 0) {
-        if (--hist[from] == 0) {
-            if (occ64) *occ64 &= ~(1ull << from);
-            else *occ32 &= ~(1u << from);
+// Once per chain-step (masks + tallies must be current).  Everything is per day or per
+// (day, class): no loop over the employee table.
+__device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int D = K.D;
+    const u64 v14 = K.n14 >= 64 ? ~0ull : ((1ull << K.n14) - 1);  // real window starts only
+    const u64 v7 = K.n7 >= 64 ? ~0ull : ((1ull << K.n7) - 1);
+    const u64 fm = *s.fmask;
+    const int nslot = __popcll(fm);
+    // phase 1: slots (one per first day), their window masks; per-day counts of the day's employee
+    for (int d = tid; d < D; d += nt) {
+        const int e = s.a[d];
+        const u64 m = s.mask[e];
+        const int f = __ffsll((long long)m) - 1;
+        const int slot = __popcll(fm & ((1ull << f) - 1ull));
+        s.dslot[d] = (unsigned char)slot;
+        const int t = __popcll(m), w = __popcll(m & K.wkend);
+        s.dayb[ES_DB_TOT + d] = (unsigned char)t;
+        s.dayb[ES_DB_WK + d] = (unsigned char)w;
+        s.dayb[ES_DB_WD + d] = (unsigned char)__popcll(m & s.wdm[d]);
+        if (f == d) {
+            s.semp[slot] = (uint16_t)e;
+            s.smask[slot] = m;
+            s.shol[slot] = hol[e];
+            s.skey[slot] = (uint16_t)((t << 5) | w);
+            u64 p14[4], p7[3];
+            es_window_planes<14, 4>(m, p14);
+            es_window_planes<7, 3>(m, p7);
+            u64* q = s.eq + slot * 4;
+            q[0] = p14[0] & p14[1] & ~p14[2] & ~p14[3] & v14;   // count == 3 (one more => H4 violation)
+            q[1] = ~p14[0] & ~p14[1] & p14[2] & ~p14[3] & v14;  // count == 4 (one less => violation gone)
+            q[2] = ~p7[0] & p7[1] & ~p7[2] & v7;                // count == 2
+            q[3] = p7[0] & p7[1] & ~p7[2] & v7;                 // count == 3
         }
     }
-    if (to >= 0) {
-        if (hist[to]++ == 0) {
-            if (occ64) *occ64 |= 1ull << to;
-            else *occ32 |= 1u << to;
+    if (tid == 0) {
+        s.skey[nslot] = 0;  // the class of every absent employee
+        s.misc[ES_NSLOT] = nslot;
+    }
+    __syncthreads();
+    // phase 2: what the day's current employee loses; class representatives
+    for (int d = tid; d < D; d += nt) {
+        const int slot = s.dslot[d];
+        const u64 m = s.smask[slot];
+        const u64* q = s.eq + slot * 4;
+        const int lossH = (int)((s.shol[slot] >> d) & 1ull) + __popcll(m & s.part[d]) + __popcll(q[1] & s.cont14[d]);
+        const int lossS = __popcll(q[3] & s.cont7[d]);
+        s.base[d] = ((unsigned)(0x8000 - lossH) << 16) | (unsigned)(0x8000 - lossS);
+    }
+    for (int c = tid; c <= nslot; c += nt) {
+        const int key = s.skey[c];
+        int r = c;
+        for (int c2 = 0; c2 < c; ++c2)
+            if ((int)s.skey[c2] == key) {
+                r = c2;
+                break;
+            }
+        s.srep[c] = (unsigned char)r;
+    }
+    __syncthreads();
+    // phase 3: memo tables.  The soft S3+S4 delta of a change move depends on the receiving
+    // employee only through its (total, weekend) class, S2 only through its count on the weekday.
+    const int ncol = nslot + 1;
+    for (int k = tid; k < D * ncol; k += nt) {
+        const int d = k / ncol, c = k - d * ncol;
+        if ((int)s.srep[c] != c) continue;
+        const int key = s.skey[c];
+        const int isw = (int)((K.wkend >> d) & 1ull);
+        const int v34 = es_s34_change(s, s.dayb[ES_DB_TOT + d], s.dayb[ES_DB_WK + d], isw, key >> 5, key & 31);
+        s.s34[d * s.ls34 + c] = (signed char)v34;
+        if (c == nslot) {  // an absent employee: no pairs, no window counts, zero days on the weekday
+            const int wd = es_weekday(K, d);
+            const int v2 = wd < 5 ? es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], 0) : 0;
+            s.baseAbs[d] = s.base[d] + (unsigned)(v34 + v2);
         }
     }
+    for (int k = tid; k < D * ES_CBINS; k += nt) {
+        const int d = k / ES_CBINS, cn = k - d * ES_CBINS;
+        const int wd = es_weekday(K, d);
+        int v = 0;  // only counts some employee actually has on that weekday (and 0) are ever looked up
+        if (wd < 5 && cn < ES_CBINS - 1 && (cn == 0 || ((s.occ2[wd] >> cn) & 1u)))
+            v = es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], cn);
+        s.s2t[k] = (signed char)v;
+    }
+    __syncthreads();
 }
 
-__device__ void es_set_mask(const EsSmem& s, const EsConst& K, int e, u64 m2) {
-    const u64 m = s.mask[e];
-    const int t = __popcll(m), t2 = __popcll(m2);
-    const int w = __popcll(m & K.wkend), w2 = __popcll(m2 & K.wkend);
-    if (t != t2 || w != w2) {
-        es_hist_move(s.histT, nullptr, s.occT, t >= 1 ? t : -1, t2 >= 1 ? t2 : -1);
-        es_hist_move(s.histW, s.occW, nullptr, t >= 1 ? w : -1, t2 >= 1 ? w2 : -1);
-        s.misc[ES_PRESENT] += (t2 >= 1) - (t >= 1);
+// ------------------------------------------------------------------ move deltas
+// Packed candidate value v = (0x8000 + dhard) << 16 | (0x8000 + dsoft): one unsigned compare
+// orders candidates lexicographically by (dhard, dsoft).
+__device__ __forceinline__ int es_v_dh(unsigned int v) { return (int)(v >> 16) - 0x8000; }
+__device__ __forceinline__ int es_v_ds(unsigned int v) { return (int)(v & 0xffffu) - 0x8000; }
+
+// change: day d goes to the PRESENT employee of `slot` (not the day's current one)
+__device__ __forceinline__ unsigned int es_change_present_v(const EsSmem& s, int d, int slot) {
+    const u64 m = s.smask[slot];
+    const u64* q = s.eq + slot * 4;
+    const int gh = (int)((s.shol[slot] >> d) & 1ull) + __popcll(m & s.part[d]) + __popcll(q[0] & s.cont14[d]);
+    const int gs = __popcll(q[2] & s.cont7[d]);
+    const int cn = __popcll(m & s.wdm[d]);
+    return s.base[d] + ((unsigned)gh << 16) +
+           (unsigned)(gs + (int)s.s2t[d * ES_CBINS + cn] + (int)s.s34[d * s.ls34 + (int)s.srep[slot]]);
+}
+
+// change: day d goes to an ABSENT employee whose holiday mask is hol
+__device__ __forceinline__ unsigned int es_change_absent_v(const EsSmem& s, int d, u64 hol) {
+    return s.baseAbs[d] + ((unsigned)((hol >> d) & 1ull) << 16);
+}
+
+// swap: days d1 < d2 exchange employees (different).
+__device__ __forceinline__ unsigned int es_swap_v(const EsSmem& s, const EsConst& K, int d1, int d2) {
+    const int s1 = s.dslot[d1], s2 = s.dslot[d2];
+    const u64 b1 = 1ull << d1, b2 = 1ull << d2;
+    const u64 m1 = s.smask[s1], m2 = s.smask[s2];
+    const u64* q1 = s.eq + s1 * 4;
+    const u64* q2 = s.eq + s2 * 4;
+    const u64 h1 = s.shol[s1], h2 = s.shol[s2];
+    // windows holding exactly one of the two days change count by one for each employee
+    const u64 c14a = s.cont14[d1], c14b = s.cont14[d2], c7a = s.cont7[d1], c7b = s.cont7[d2];
+    const u64 only14a = c14a & ~c14b, only14b = c14b & ~c14a, only7a = c7a & ~c7b, only7b = c7b & ~c7a;
+    int dh = (int)((h1 >> d2) & 1ull) - (int)((h1 >> d1) & 1ull) + (int)((h2 >> d1) & 1ull) -
+             (int)((h2 >> d2) & 1ull);
+    // H2/H3 pairs: e1 leaves d1 and lands on d2 (its other days: m1 without d1), e2 the reverse
+    dh += __popcll((m1 & ~b1) & s.part[d2]) - __popcll(m1 & s.part[d1]);
+    dh += __popcll((m2 & ~b2) & s.part[d1]) - __popcll(m2 & s.part[d2]);
+    // H4: e1 loses a day in windows with only d1 (count 4 -> 3), gains in windows with only d2
+    dh += __popcll(q1[0] & only14b) - __popcll(q1[1] & only14a);
+    dh += __popcll(q2[0] & only14a) - __popcll(q2[1] & only14b);
+    int ds = __popcll(q1[2] & only7b) - __popcll(q1[3] & only7a);
+    ds += __popcll(q2[2] & only7a) - __popcll(q2[3] & only7b);
+    const u64 w1 = s.wdm[d1], w2 = s.wdm[d2];
+    if (w1 != w2) {
+        // the two weekdays are distinct histograms, so their deltas are independent
+        if (w1) ds += es_s2_delta(s, es_weekday(K, d1), __popcll(m1 & w1), __popcll(m2 & w1));
+        if (w2) ds += es_s2_delta(s, es_weekday(K, d2), __popcll(m2 & w2), __popcll(m1 & w2));
     }
-    for (int wd = 0; wd < 5; ++wd) {
-        const int c = __popcll(m & K.wd[wd]), c2 = __popcll(m2 & K.wd[wd]);
-        if (c == c2) continue;
-        es_hist_move(s.hist2 + wd * ES_CBINS, &s.occ2[wd], nullptr, c >= 1 ? c : -1,
-                     c2 >= 1 ? c2 : -1);
-        s.misc[ES_DISTINCT0 + wd] += (c2 >= 1) - (c >= 1);
+    const int k1 = (K.wkend & b1) ? 1 : 0, k2 = (K.wkend & b2) ? 1 : 0;
+    if (k1 != k2) {  // totals (S3) unchanged; weekend counts move between the two employees
+        const int present = s.misc[ES_PRESENT];
+        const int x1 = s.dayb[ES_DB_WK + d1], x2 = s.dayb[ES_DB_WK + d2];
+        EsAdj W;
+        W.add(x1, -1);
+        W.add(x1 - k1 + k2, +1);
+        W.add(x2, -1);
+        W.add(x2 + k1 - k2, +1);
+        const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
+        ds += es_spread(occW, present) - es_spread((u64)*s.occW, present);
     }
-    s.mask[e] = m2;
+    return ((unsigned)(0x8000 + dh) << 16) | (unsigned)(0x8000 + ds);
 }
 
 // move id: change (d, e) -> d*E + e ; swap (d1<d2) -> D*E + tri(d1,d2)
 __device__ __forceinline__ int es_tri_index(int D, int d1, int d2) {
     return d1 * D - d1 * (d1 + 1) / 2 + (d2 - d1 - 1);
 }
+// inverse of es_tri_index
+__device__ __forceinline__ void es_tri_decode(int D, int r, int& d1, int& d2) {
+    const float b = (float)(2 * D - 1);
+    int x = (int)((b - sqrtf(b * b - 8.0f * (float)r)) * 0.5f);
+    x = max(0, min(x, D - 2));
+    while (x > 0 && x * D - x * (x + 1) / 2 > r) --x;
+    while (x < D - 2 && (x + 1) * D - (x + 1) * (x + 2) / 2 <= r) ++x;
+    d1 = x;
+    d2 = x + 1 + (r - (x * D - x * (x + 1) / 2));
+}
 
-__device__ __forceinline__ long long es_key(int dh, int ds, int id) {
-    return ((long long)(dh + 32768) << 44) | ((long long)(ds + 32768) << 24) | (long long)id;
+// key = v << 24 | move id  (id < 2^24: 64 days x 65535 employees + swaps)
+__device__ __forceinline__ long long es_key(unsigned int v, int id) {
+    return (long long)(((u64)v << 24) | (u64)(unsigned)id);
 }
 
 __device__ __forceinline__ long long es_block_min(long long key, u64* red) {
@@ -588,6 +582,112 @@ __device__ __forceinline__ long long es_block_min(long long key, u64* red) {
     return out;
 }
 
+// The neighbourhood scan of one chain-step: every non-identity candidate gets its exact packed
+// (dhard, dsoft); returns this thread's minimum key.  Three passes:
+//   A  change moves to PRESENT employees  (day x slot; full mask arithmetic)
+//   B  change moves to ABSENT employees   (thread per employee, loop over days; the delta is the
+//      per-day table value plus the employee's holiday bit)
+//   C  swaps
+template <bool DUMP>
+__device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol,
+                                             long long* dump_h, long long* dump_s) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int D = K.D, E = K.E;
+    const int nslot = s.misc[ES_NSLOT];
+    long long key = ES_KEY_INF;
+    {   // A
+        const int nA = nslot * D;
+        int d = tid / nslot, slot = tid - d * nslot;
+        const int dd = nt / nslot, dsl = nt - dd * nslot;
+        for (int k = tid; k < nA; k += nt) {
+            const int id = d * E + (int)s.semp[slot];
+            if ((int)s.dslot[d] != slot) {
+                const unsigned int v = es_change_present_v(s, d, slot);
+                const long long k2 = es_key(v, id);
+                key = k2 < key ? k2 : key;
+                if (DUMP) {
+                    dump_h[id] = es_v_dh(v);
+                    dump_s[id] = es_v_ds(v);
+                }
+            } else if (DUMP) {
+                dump_h[id] = INT64_MAX;
+                dump_s[id] = INT64_MAX;
+            }
+            slot += dsl;
+            d += dd;
+            if (slot >= nslot) {
+                slot -= nslot;
+                ++d;
+            }
+        }
+    }
+    // B
+    for (int e = tid; e < E; e += nt) {
+        if (s.mask[e]) continue;
+        const u64 h = hol[e];
+        unsigned int bv = 0xffffffffu;
+        int bd = 0;
+        const unsigned int hlo = (unsigned int)h, hhi = (unsigned int)(h >> 32);
+        const int Dlo = D < 32 ? D : 32;
+#pragma unroll 4
+        for (int d = 0; d < Dlo; ++d) {
+            const unsigned int v = s.baseAbs[d] + (((hlo >> d) & 1u) << 16);
+            if (v < bv) {
+                bv = v;
+                bd = d;
+            }
+            if (DUMP) {
+                dump_h[d * E + e] = es_v_dh(v);
+                dump_s[d * E + e] = es_v_ds(v);
+            }
+        }
+#pragma unroll 4
+        for (int d = 32; d < D; ++d) {
+            const unsigned int v = s.baseAbs[d] + (((hhi >> (d - 32)) & 1u) << 16);
+            if (v < bv) {
+                bv = v;
+                bd = d;
+            }
+            if (DUMP) {
+                dump_h[d * E + e] = es_v_dh(v);
+                dump_s[d * E + e] = es_v_ds(v);
+            }
+        }
+        const long long k2 = es_key(bv, bd * E + e);
+        key = k2 < key ? k2 : key;
+    }
+    {   // C
+        const int n_change = D * E, n_swap = D * (D - 1) / 2;
+        for (int r = tid; r < n_swap; r += nt) {
+            int d1, d2;
+            es_tri_decode(D, r, d1, d2);
+            const int id = n_change + r;
+            if (s.dslot[d1] != s.dslot[d2]) {
+                const unsigned int v = es_swap_v(s, K, d1, d2);
+                const long long k2 = es_key(v, id);
+                key = k2 < key ? k2 : key;
+                if (DUMP) {
+                    dump_h[id] = es_v_dh(v);
+                    dump_s[id] = es_v_ds(v);
+                }
+            } else if (DUMP) {
+                dump_h[id] = INT64_MAX;
+                dump_s[id] = INT64_MAX;
+            }
+        }
+    }
+    return key;
+}
+
+// per-day constants of the handle: part | cont14 | cont7 from the host table, weekday masks
+__device__ __forceinline__ void es_load_consts(const EsSmem& s, const EsConst& K, const u64* __restrict__ dayconst) {
+    for (int k = threadIdx.x; k < 192; k += blockDim.x) s.part[k] = dayconst[k];
+    for (int d = threadIdx.x; d < 64; d += blockDim.x) {
+        const int wd = (K.start_wd + d) % 7;
+        s.wdm[d] = (d < K.D && wd < 5) ? K.wd[wd] : 0ull;
+    }
+}
+
 // ------------------------------------------------------------------ the step kernel (K5)
 __global__ void es_step_kernel(EsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -595,8 +695,8 @@ __global__ void es_step_kernel(EsParams p) {
     const EsSmem s = es_carve(smem_raw, K.D, K.E);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int D = K.D, E = K.E;
-    const int n_change = D * E, n_swap = D * (D - 1) / 2, n_moves = n_change + n_swap;
-    for (int k = tid; k < 192; k += nt) s.part[k] = p.dayconst[k];  // part | cont14 | cont7
+    const int n_change = D * E, n_swap = D * (D - 1) / 2;
+    es_load_consts(s, K, p.dayconst);
 
     for (;;) {
         __syncthreads();
@@ -629,54 +729,19 @@ __global__ void es_step_kernel(EsParams p) {
                 break;
             }
             es_prepare(s, K, p.hol);
-            long long key = ES_KEY_INF;
-            unsigned int nscored = 0;
-            for (int id = tid; id < n_moves; id += nt) {
-                int dh, ds;
-                bool ok;
-                if (id < n_change) {
-                    const int d = id / E, e = id - d * E;
-                    ok = (s.a[d] != e);
-                    if (ok) es_change_delta(s, K, p.hol, d, e, dh, ds);
-                } else {
-                    // decode the triangular index (d1 < d2)
-                    int r = id - n_change, d1 = 0;
-                    while (r >= D - 1 - d1) {
-                        r -= D - 1 - d1;
-                        ++d1;
-                    }
-                    const int d2 = d1 + 1 + r;
-                    ok = (s.a[d1] != s.a[d2]);
-                    if (ok) es_swap_delta(s, K, p.hol, d1, d2, dh, ds);
-                }
-                if (p.dump_h) {
-                    p.dump_h[id] = ok ? (long long)dh : INT64_MAX;
-                    p.dump_s[id] = ok ? (long long)ds : INT64_MAX;
-                }
-                if (ok) {
-                    ++nscored;
-                    const long long k2 = es_key(dh, ds, id);
-                    key = k2 < key ? k2 : key;
-                }
-            }
+            // non-identity candidates: every (day, employee != current) + every day pair held by
+            // two different employees -- each of them is evaluated by es_scan
+            scored += (unsigned long long)(n_change - D) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
+            long long key = p.dump_h ? es_scan<true>(s, K, p.hol, p.dump_h, p.dump_s)
+                                     : es_scan<false>(s, K, p.hol, nullptr, nullptr);
             key = es_block_min(key, s.red);
-            {   // count the candidates scored (block sum through the same scratch)
-                unsigned int c = nscored;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                if ((tid & 31) == 0) atomicAdd((unsigned int*)&s.misc[ES_BCAST + 1], c);
-                __syncthreads();
-                scored += (unsigned int)s.misc[ES_BCAST + 1];
-                __syncthreads();
-                if (tid == 0) s.misc[ES_BCAST + 1] = 0;
-            }
             if (p.dump_h) break;
             if (key == ES_KEY_INF) {  // empty neighbourhood, local_search.rs:336-338
                 status = 3;
                 break;
             }
-            const int dh = (int)((key >> 44) & 0xffff) - 32768;
-            const int ds = (int)((key >> 24) & 0xfffff) - 32768;
+            const unsigned int v = (unsigned int)((u64)key >> 24);
+            const int dh = es_v_dh(v), ds = es_v_ds(v);
             const int id = (int)(key & 0xffffff);
             const bool improved = dh < 0 || (dh == 0 && ds < 0);  // lexicographic (hard, soft)
             if (!improved) {
@@ -695,22 +760,19 @@ __global__ void es_step_kernel(EsParams p) {
                 if (id < n_change) {
                     const int d = id / E, e = id - d * E, eo = s.a[d];
                     const u64 bit = 1ull << d;
-                    es_set_mask(s, K, eo, s.mask[eo] & ~bit);
-                    es_set_mask(s, K, e, s.mask[e] | bit);
+                    s.mask[eo] &= ~bit;
+                    s.mask[e] |= bit;
                     s.a[d] = (uint16_t)e;
                     kind = 0;
                     x = (unsigned)d;
                     y = (unsigned)e;
                 } else {
-                    int r = id - n_change, d1 = 0;
-                    while (r >= D - 1 - d1) {
-                        r -= D - 1 - d1;
-                        ++d1;
-                    }
-                    const int d2 = d1 + 1 + r, e1 = s.a[d1], e2 = s.a[d2];
+                    int d1, d2;
+                    es_tri_decode(D, id - n_change, d1, d2);
+                    const int e1 = s.a[d1], e2 = s.a[d2];
                     const u64 x2 = (1ull << d1) | (1ull << d2);
-                    es_set_mask(s, K, e1, s.mask[e1] ^ x2);
-                    es_set_mask(s, K, e2, s.mask[e2] ^ x2);
+                    s.mask[e1] ^= x2;
+                    s.mask[e2] ^= x2;
                     s.a[d1] = (uint16_t)e2;
                     s.a[d2] = (uint16_t)e1;
                     kind = 1;
@@ -736,6 +798,7 @@ __global__ void es_step_kernel(EsParams p) {
                 for (int k = tid; k < p.stride; k += nt)
                     p.best_a[(size_t)chain * p.stride + k] = s.a[k];
             }
+            if (it + 1 < p.max_steps) es_tally<false>(s, K, p.hol);  // tallies of the new state
         }
         __syncthreads();
         if (p.dump_h) continue;
@@ -789,25 +852,29 @@ __global__ void es_eval_kernel(EsParams p, int chain, int kind, const uint2* __r
     const EsSmem s = es_carve(smem_raw, p.K.D, p.K.E);
     for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
         s.a[k] = p.a[(size_t)chain * p.stride + k];
-    for (int k = threadIdx.x; k < 192; k += blockDim.x) s.part[k] = p.dayconst[k];
+    es_load_consts(s, p.K, p.dayconst);
     __syncthreads();
     int hard, soft;
     es_build(s, p.K, p.hol, hard, soft);
     es_prepare(s, p.K, p.hol);
     for (unsigned long long k = threadIdx.x; k < n_moves; k += blockDim.x) {
         const uint2 mv = moves[k];
-        int dh = 0, ds = 0;
+        unsigned int v = 0;
         bool ok;
         if (kind == 0) {
-            ok = s.a[mv.x] != mv.y;
-            if (ok) es_change_delta(s, p.K, p.hol, (int)mv.x, (int)mv.y, dh, ds);
+            const int d = (int)mv.x, en = (int)mv.y;
+            ok = s.a[d] != en;
+            if (ok) {
+                const u64 m = s.mask[en];
+                v = m ? es_change_present_v(s, d, es_slot_of(s, m)) : es_change_absent_v(s, d, p.hol[en]);
+            }
         } else {
             const int d1 = (int)min(mv.x, mv.y), d2 = (int)max(mv.x, mv.y);
             ok = d1 != d2 && s.a[d1] != s.a[d2];
-            if (ok) es_swap_delta(s, p.K, p.hol, d1, d2, dh, ds);
+            if (ok) v = es_swap_v(s, p.K, d1, d2);
         }
-        dh_out[k] = ok ? (long long)dh : INT64_MAX;
-        ds_out[k] = ok ? (long long)ds : INT64_MAX;
+        dh_out[k] = ok ? (long long)es_v_dh(v) : INT64_MAX;
+        ds_out[k] = ok ? (long long)es_v_ds(v) : INT64_MAX;
     }
 }
 
