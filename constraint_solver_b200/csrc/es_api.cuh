@@ -18,7 +18,7 @@ struct cs_es_handle {
     uint16_t* d_a = nullptr;
     uint16_t* d_best_a = nullptr;
     u64* d_hol = nullptr;
-    u64* d_dayconst = nullptr;  // [3][64] PART, CONT14, CONT7
+    u64* d_dayconst = nullptr;  // [3][64] PART, CONT14, CONT7, then the swap table (u16 per swap)
     EsChainState* d_st = nullptr;
     EsTraceEntry* d_trace = nullptr;
     unsigned int* d_work = nullptr;
@@ -238,6 +238,14 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
                 dayc[q[0]] |= 1ull << q[1];
                 dayc[q[1]] |= 1ull << q[0];
             }
+        }
+        {   // swap r -> (d1 << 8 | d2), enumeration order d1 < d2 row-major; appended as u16
+            const size_t n_swap = (size_t)D * (D - 1) / 2;
+            dayc.resize(3 * 64 + (n_swap + 3) / 4 + 1, 0ull);
+            uint16_t* tri = (uint16_t*)(dayc.data() + 192);
+            size_t r = 0;
+            for (int d1 = 0; d1 < D; ++d1)
+                for (int d2 = d1 + 1; d2 < D; ++d2) tri[r++] = (uint16_t)((d1 << 8) | d2);
         }
         std::vector<u64> hol(E, 0ull);
         for (uint64_t k = 0; k < n_hol; ++k) {

@@ -38,8 +38,6 @@ constexpr int ES_CBINS = 12;   // per-weekday count bins 0..11 (a weekday occurs
 constexpr int ES_TBINS = 66;   // total-days bins 0..65
 constexpr int ES_WBINS = 24;   // weekend-day bins 0..23
 constexpr long long ES_KEY_INF = 0x7fffffffffffffffll;
-constexpr int ES_KEYS = 66 * 32;  // (total days 0..65) x (weekend days 0..31)
-constexpr int ES_MAXCLS = 68;
 
 struct EsConst {
     int D, E, start_wd, n14, n7;
@@ -77,7 +75,10 @@ struct EsParams {
     const unsigned int* skip;  // optional [chains]: 1 = leave the chain alone (ILS)
 };
 
-// per-chain shared state.  NS = min(E, D) bounds the number of PRESENT employees ("slots").
+// per-chain shared state.  NS = min(E, D) bounds the number of PRESENT employees ("slots");
+// DP = D rounded up to 4 sizes the per-day arrays.
+constexpr int ES_TCOLS = 12;  // distinct total-day values among present employees (sum <= 64 => <= 10)
+constexpr int ES_WCOLS = 8;   // distinct weekend-day values (0 included; sum <= 20 => <= 6)
 struct EsSmem {
     u64* mask;          // [E]
     uint16_t* a;        // [stride]
@@ -90,58 +91,64 @@ struct EsSmem {
     u64* fmask;         // [1]  bit d: day d is the FIRST day of its employee (one bit per present employee)
     int* misc;          // [16] present, distinct[5], hard, soft, ...
     u64* red;           // [40] reduction scratch
-    u64* part;          // [64] H2/H3 partner-day mask per day
-    u64* cont14;        // [64] 14-day window starts whose window contains the day
-    u64* cont7;         // [64]
-    u64* wdm;           // [64] days on the same weekday as d (0 for weekend days)
+    u64* part;          // [DP] H2/H3 partner-day mask per day
+    u64* cont14;        // [DP] 14-day window starts whose window contains the day
+    u64* cont7;         // [DP]
+    u64* wdm;           // [DP] days on the same weekday as d (0 for weekend days)
     u64* eq;            // [NS][4] per slot: EQ3_14, EQ4_14, EQ2_7, EQ3_7 ("count == k" window starts)
     u64* smask;         // [NS] day mask of the slot's employee
     u64* shol;          // [NS] its holiday mask
     uint16_t* semp;     // [NS] its employee index
-    uint16_t* skey;     // [NS+1] (total days << 5 | weekend days); [nslot] = 0 = an absent employee
-    unsigned char* srep;   // [NS+1] lowest column with the same key (S3+S4 class representative)
-    unsigned char* dslot;  // [64] slot of the day's current employee
-    unsigned char* dayb;   // [3][64] per day, for its current employee: total, weekend, weekday count
-    unsigned int* base;    // [64] packed (0x8000 - lossH) << 16 | (0x8000 - lossS1) of the day's employee
-    unsigned int* baseAbs; // [64] packed value of giving day d to an absent employee without a holiday
-    signed char* s34;      // [64][ls34] S3+S4 delta of giving day d to an employee of column's class
-    signed char* s2t;      // [64][ES_CBINS] S2 delta of giving day d to an employee with cn days on that weekday
-    int ns, ls34;
+    unsigned char* srk;    // [NS][2] rank of its total-day / weekend-day count among the values in use
+    unsigned char* val;    // [ES_TCOLS + ES_WCOLS] rank -> value (total days | weekend days)
+    unsigned char* dwd;    // [DP] weekday of the day (0 = Monday)
+    unsigned char* dslot;  // [DP] slot of the day's current employee
+    unsigned char* dayb;   // [3][DP] per day, for its current employee: total, weekend, weekday count
+    unsigned int* base;    // [DP] packed (0x8000 - lossH) << 16 | (0x8000 - lossS1) of the day's employee
+    unsigned int* baseW;   // [DP] absent receiver without a holiday: (dh + 64) << 15 | (ds + 256) << 6 | d
+    signed char* s2t;      // [DP][ES_CBINS] S2 delta of giving day d to an employee with cn days on that weekday
+    signed char* s3t;      // [DP][ES_TCOLS] S3 delta ... to a present employee whose total has rank j
+    signed char* s4t;      // [DP][ES_WCOLS] S4 delta ... to a present employee whose weekend count has rank j
+    int ns, dp;
 };
 
 struct EsLayout {
-    size_t mask, a, hist, occ, occT, fmask, misc, red, day, eq, smask, shol, semp, skey, srep, dslot, dayb, base,
-        baseAbs, s34, s2t, total;
-    int ns, ls34;
+    size_t mask, a, hist, occ, occT, fmask, misc, red, day, eq, smask, shol, semp, srk, val, dwd, dslot, dayb, base,
+        baseW, s2t, s3t, s4t, total;
+    int ns, dp;
 };
 __host__ __device__ inline size_t es_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline EsLayout es_layout(int D, int E) {
     EsLayout L;
     L.ns = E < D ? E : D;
     if (L.ns < 1) L.ns = 1;
-    L.ls34 = (L.ns + 1 + 3) & ~3;
+    L.dp = (D + 3) & ~3;
+    const size_t dp = (size_t)L.dp;
     size_t o = 0;
     L.mask = o;    o += (size_t)E * 8;
     L.occT = o;    o += 8;
     L.fmask = o;   o += 8;
     L.red = o;     o += 40 * 8;
-    L.day = o;     o += 4 * 64 * 8;
+    L.day = o;     o += 4 * dp * 8;
     L.eq = o;      o += (size_t)L.ns * 4 * 8;
     L.smask = o;   o += (size_t)L.ns * 8;
     L.shol = o;    o += (size_t)L.ns * 8;
+    o = es_align(o, 16);
+    L.baseW = o;   o += dp * 4;  // read as uint4
+    L.base = o;    o += dp * 4;
     L.misc = o;    o += 16 * 4;
     L.occ = o;     o = es_align(o + 6 * 4, 8);
-    L.base = o;    o += 64 * 4;
-    L.baseAbs = o; o += 64 * 4;
     L.hist = o;    o = es_align(o + (5 * ES_CBINS + ES_TBINS + ES_WBINS) * 2, 8);
     L.a = o;       o = es_align(o + (size_t)(D + 1) * 2, 8);
     L.semp = o;    o = es_align(o + (size_t)L.ns * 2, 8);
-    L.skey = o;    o = es_align(o + (size_t)(L.ns + 1) * 2, 8);
-    L.srep = o;    o = es_align(o + (size_t)(L.ns + 1), 8);
-    L.dslot = o;   o += 64;
-    L.dayb = o;    o += 3 * 64;
-    L.s34 = o;     o = es_align(o + (size_t)64 * L.ls34, 8);
-    L.s2t = o;     o = es_align(o + 64 * ES_CBINS, 8);
+    L.srk = o;     o = es_align(o + (size_t)L.ns * 2, 8);
+    L.val = o;     o = es_align(o + ES_TCOLS + ES_WCOLS, 8);
+    L.dwd = o;     o += dp;
+    L.dslot = o;   o += dp;
+    L.dayb = o;    o += 3 * dp;
+    L.s2t = o;     o += dp * ES_CBINS;
+    L.s3t = o;     o += dp * ES_TCOLS;
+    L.s4t = o;     o += dp * ES_WCOLS;
     L.total = es_align(o, 16);
     return L;
 }
@@ -152,7 +159,7 @@ __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     const EsLayout L = es_layout(D, E);
     EsSmem s;
     s.ns = L.ns;
-    s.ls34 = L.ls34;
+    s.dp = L.dp;
     s.mask = (u64*)(p + L.mask);
     s.a = (uint16_t*)(p + L.a);
     s.hist2 = (uint16_t*)(p + L.hist);
@@ -165,135 +172,93 @@ __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     s.misc = (int*)(p + L.misc);
     s.red = (u64*)(p + L.red);
     s.part = (u64*)(p + L.day);
-    s.cont14 = s.part + 64;
-    s.cont7 = s.cont14 + 64;
-    s.wdm = s.cont7 + 64;
+    s.cont14 = s.part + L.dp;
+    s.cont7 = s.cont14 + L.dp;
+    s.wdm = s.cont7 + L.dp;
     s.eq = (u64*)(p + L.eq);
     s.smask = (u64*)(p + L.smask);
     s.shol = (u64*)(p + L.shol);
     s.semp = (uint16_t*)(p + L.semp);
-    s.skey = (uint16_t*)(p + L.skey);
-    s.srep = p + L.srep;
+    s.srk = p + L.srk;
+    s.val = p + L.val;
+    s.dwd = p + L.dwd;
     s.dslot = p + L.dslot;
     s.dayb = p + L.dayb;
     s.base = (unsigned int*)(p + L.base);
-    s.baseAbs = (unsigned int*)(p + L.baseAbs);
-    s.s34 = (signed char*)(p + L.s34);
+    s.baseW = (unsigned int*)(p + L.baseW);
     s.s2t = (signed char*)(p + L.s2t);
+    s.s3t = (signed char*)(p + L.s3t);
+    s.s4t = (signed char*)(p + L.s4t);
     return s;
 }
 
 enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10, ES_SAME = 11 };
-enum { ES_DB_TOT = 0, ES_DB_WK = 64, ES_DB_WD = 128 };
-
-// ------------------------------------------------------------------ per-employee terms
-__device__ __forceinline__ int es_pair_terms(u64 m, u64 hol, const EsConst& K) {
-    const u64 m1 = m >> 1, m7 = m >> 7, m8 = m >> 8;
-    return __popcll(m & hol) + __popcll(m & m1) + __popcll(m & m7 & K.satf) +
-           __popcll(m & m8 & K.satf) + __popcll(m1 & m7 & K.satf) + __popcll(m1 & m8 & K.satf);
-}
-
-// windows w in [lo, hi]: #{popc(m & W<<w) > thr}
-__device__ __forceinline__ int es_win_viol(u64 m, u64 W, int lo, int hi, int thr) {
-    int v = 0;
-    for (int w = lo; w <= hi; ++w) v += (__popcll(m & (W << w)) > thr);
-    return v;
-}
-
-// (hard, S1) of employee mask m over all windows
-__device__ __forceinline__ void es_emp_full(u64 m, u64 hol, const EsConst& K, int& hard, int& s1) {
-    hard = es_pair_terms(m, hol, K) + es_win_viol(m, 0x3fffull, 0, K.n14 - 1, 3);
-    s1 = es_win_viol(m, 0x7full, 0, K.n7 - 1, 2);
-}
+constexpr unsigned int ES_W_PAD = 0x7fff0000u;  // larger than any packed absent-candidate value, no overflow on +hol
 
 // ------------------------------------------------------------------ histogram helpers
-// up to four (bin, +-1) histogram adjustments, always four slots so everything stays in
-// registers (unused slots carry delta 0 on a valid bin)
-struct EsAdj {
-    int b0, b1, b2, b3, d0, d1, d2, d3, n;
-    __device__ __forceinline__ EsAdj() : b0(0), b1(0), b2(0), b3(0), d0(0), d1(0), d2(0), d3(0), n(0) {}
-    __device__ __forceinline__ void add(int b, int delta) {
-        if (n == 0) { b0 = b; d0 = delta; }
-        else if (n == 1) { b1 = b; d1 = delta; }
-        else if (n == 2) { b2 = b; d2 = delta; }
-        else { b3 = b; d3 = delta; }
-        ++n;
+// Occupancy bitset after one member leaves bin r0, one leaves r1 (r1 < 0: nobody), one enters
+// a0 (a0 < 0: nobody) and one enters a1.  hist holds the current member count per bin.
+__device__ __forceinline__ u64 es_occ_move(const uint16_t* hist, u64 occ, int r0, int r1, int a0, int a1) {
+    int c0 = (int)hist[r0] - 1;
+    if (r1 >= 0) {
+        const int same = (r1 == r0) ? 1 : 0;
+        c0 -= same;
+        if ((int)hist[r1] - 1 - same <= 0) occ &= ~(1ull << r1);
     }
-};
-
-__device__ __forceinline__ u64 es_occ_one(const uint16_t* hist, u64 occ, int b, const EsAdj& A) {
-    const int tot = (A.b0 == b ? A.d0 : 0) + (A.b1 == b ? A.d1 : 0) + (A.b2 == b ? A.d2 : 0) +
-                    (A.b3 == b ? A.d3 : 0);
-    const int c = (int)hist[b] + tot;
-    const u64 bit = 1ull << b;
-    return c > 0 ? (occ | bit) : (occ & ~bit);
+    if (c0 <= 0) occ &= ~(1ull << r0);
+    if (a0 >= 0) occ |= 1ull << a0;
+    return occ | (1ull << a1);
 }
-
-// occupancy bitset after applying the adjustments to the histogram
-__device__ __forceinline__ u64 es_occ_after(const uint16_t* hist, u64 occ, const EsAdj& A) {
-    occ = es_occ_one(hist, occ, A.b0, A);
-    occ = es_occ_one(hist, occ, A.b1, A);
-    occ = es_occ_one(hist, occ, A.b2, A);
-    occ = es_occ_one(hist, occ, A.b3, A);
-    return occ;
+__device__ __forceinline__ unsigned int es_occ_move32(const uint16_t* hist, unsigned int occ, int r0, int r1, int a0,
+                                                      int a1) {
+    int c0 = (int)hist[r0] - 1;
+    if (r1 >= 0) {
+        const int same = (r1 == r0) ? 1 : 0;
+        c0 -= same;
+        if ((int)hist[r1] - 1 - same <= 0) occ &= ~(1u << r1);
+    }
+    if (c0 <= 0) occ &= ~(1u << r0);
+    if (a0 >= 0) occ |= 1u << a0;
+    return occ | (1u << a1);
 }
 
 __device__ __forceinline__ int es_spread(u64 occ, int members) {  // max-min, lib.rs:349,363
     if (members < 2 || occ == 0) return 0;
     return (63 - __clzll((long long)occ)) - (__ffsll((long long)occ) - 1);
 }
+__device__ __forceinline__ int es_spread32(unsigned int occ, int members) {
+    if (members < 2 || occ == 0) return 0;
+    return (31 - __clz((int)occ)) - (__ffs((int)occ) - 1);
+}
 
 __device__ __forceinline__ int es_s2_term(unsigned int occ, int distinct) {  // lib.rs:206-214
     return (distinct >= 2 && occ) ? (__ffs((int)occ) - 1) : 0;
 }
 
-// weekday-affinity delta on weekday wd when employee counts change: cm (count c -> c-1) and
-// cp (count c -> c+1); pass -1 to skip one side.
+// weekday-affinity delta on weekday wd when one employee's count there goes cm -> cm-1
+// (cm >= 1) and another's goes cp -> cp+1 (cp >= 0)
 __device__ __forceinline__ int es_s2_delta(const EsSmem& s, int wd, int cm, int cp) {
-    EsAdj A;
-    int distinct = s.misc[ES_DISTINCT0 + wd];
-    const int old = es_s2_term(s.occ2[wd], distinct);
-    if (cm >= 1) {
-        A.add(cm, -1);
-        if (cm - 1 >= 1) A.add(cm - 1, +1);
-        else --distinct;
-    }
-    if (cp >= 0) {
-        if (cp >= 1) A.add(cp, -1);
-        else ++distinct;
-        A.add(cp + 1, +1);
-    }
-    const unsigned int occ = (unsigned int)es_occ_after(s.hist2 + wd * ES_CBINS, s.occ2[wd], A);
-    return es_s2_term(occ, distinct) - old;
+    const int distinct = s.misc[ES_DISTINCT0 + wd];
+    const unsigned int occ0 = s.occ2[wd];
+    const unsigned int occ = es_occ_move32(s.hist2 + wd * ES_CBINS, occ0, cm, cp >= 1 ? cp : -1,
+                                           cm - 1 >= 1 ? cm - 1 : -1, cp + 1);
+    return es_s2_term(occ, distinct - (cm == 1) + (cp == 0)) - es_s2_term(occ0, distinct);
 }
 
-__device__ __forceinline__ int es_weekday(const EsConst& K, int d) { return (K.start_wd + d) % 7; }
-
-// S3 + S4 delta when a day (weekend flag isw) moves from an employee with (to, wo) total /
-// weekend days to one with (tn, wn); lib.rs:345-365, min/max over PRESENT employees only.
-__device__ __forceinline__ int es_s34_change(const EsSmem& s, int to, int wo, int isw, int tn, int wn) {
-    int present = s.misc[ES_PRESENT];
-    const int oldT = es_spread(*s.occT, present), oldW = es_spread((u64)*s.occW, present);
-    EsAdj T, W;
-    T.add(to, -1);
-    W.add(wo, -1);
-    if (to - 1 >= 1) {
-        T.add(to - 1, +1);
-        W.add(wo - isw, +1);
-    } else {
-        --present;
-    }
-    if (tn >= 1) {
-        T.add(tn, -1);
-        W.add(wn, -1);
-    } else {
-        ++present;
-    }
-    T.add(tn + 1, +1);
-    W.add(wn + isw, +1);
-    const u64 occT = es_occ_after(s.histT, *s.occT, T);
-    const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
-    return es_spread(occT, present) - oldT + es_spread(occW, present) - oldW;
+// S3 delta (max-min of total days over PRESENT employees, lib.rs:345-351) when a day moves from
+// an employee with `to` days to one with `tn` days (0 = absent so far)
+__device__ __forceinline__ int es_s3_delta(const EsSmem& s, int to, int tn) {
+    const int present = s.misc[ES_PRESENT];
+    const u64 occ = es_occ_move(s.histT, *s.occT, to, tn >= 1 ? tn : -1, to - 1 >= 1 ? to - 1 : -1, tn + 1);
+    return es_spread(occ, present - (to == 1) + (tn == 0)) - es_spread(*s.occT, present);
+}
+// S4 delta (weekend days, lib.rs:354-365): the day (weekend flag isw) leaves an employee with
+// (to total, wo weekend) days for one with wn weekend days (absent = !rpresent, wn = 0)
+__device__ __forceinline__ int es_s4_delta(const EsSmem& s, int to, int wo, int isw, int wn, bool rpresent) {
+    const int present = s.misc[ES_PRESENT];
+    const unsigned int occ = es_occ_move32(s.histW, *s.occW, wo, rpresent ? wn : -1, to - 1 >= 1 ? wo - isw : -1,
+                                           wn + isw);
+    return es_spread32(occ, present - (to == 1) + (rpresent ? 0 : 1)) - es_spread32(*s.occW, present);
 }
 
 // ------------------------------------------------------------------ tallies and per-step tables
@@ -313,6 +278,12 @@ __device__ __forceinline__ void es_window_planes(u64 m, u64 (&pl)[PLANES]) {
             carry = t;
         }
     }
+}
+
+__device__ __forceinline__ int es_pair_terms(u64 m, u64 hol, const EsConst& K) {
+    const u64 m1 = m >> 1, m7 = m >> 7, m8 = m >> 8;
+    return __popcll(m & hol) + __popcll(m & m1) + __popcll(m & m7 & K.satf) +
+           __popcll(m & m8 & K.satf) + __popcll(m1 & m7 & K.satf) + __popcll(m1 & m8 & K.satf);
 }
 
 __device__ __forceinline__ void es_hist16_inc(uint16_t* hist2, int idx) {  // 16-bit bin through its 32-bit word
@@ -339,6 +310,8 @@ __device__ void es_tally(const EsSmem& s, const EsConst& K, const u64* __restric
         *s.fmask = 0;
     }
     __syncthreads();
+    const u64 v14 = K.n14 >= 64 ? ~0ull : ((1ull << K.n14) - 1);  // real window starts only
+    const u64 v7 = K.n7 >= 64 ? ~0ull : ((1ull << K.n7) - 1);
     for (int d = tid; d < K.D; d += nt) {
         const int e = s.a[d];
         const u64 m = s.mask[e];
@@ -359,9 +332,12 @@ __device__ void es_tally(const EsSmem& s, const EsConst& K, const u64* __restric
             atomicOr(&s.occ2[wd], 1u << c);
             atomicAdd(&s.misc[ES_DISTINCT0 + wd], 1);
         }
-        if (SCORE) {
-            int eh, es;
-            es_emp_full(m, hol[e], K, eh, es);
+        if (SCORE) {  // H1..H3 pairs + H4 (14-day windows with count > 3) ; S1 (7-day windows, count > 2)
+            u64 p14[4], p7[3];
+            es_window_planes<14, 4>(m, p14);
+            es_window_planes<7, 3>(m, p7);
+            const int eh = es_pair_terms(m, hol[e], K) + __popcll((p14[2] | p14[3]) & v14);
+            const int es = __popcll(((p7[0] & p7[1]) | p7[2]) & v7);
             atomicAdd(&s.misc[ES_HARD], eh);
             atomicAdd(&s.misc[ES_SOFT], es);
         }
@@ -382,19 +358,20 @@ __device__ void es_build(const EsSmem& s, const EsConst& K, const u64* __restric
     soft = s.misc[ES_SOFT];
     const int present = s.misc[ES_PRESENT];
     for (int wd = 0; wd < 5; ++wd) soft += es_s2_term(s.occ2[wd], s.misc[ES_DISTINCT0 + wd]);
-    soft += es_spread(*s.occT, present) + es_spread((u64)*s.occW, present);
+    soft += es_spread(*s.occT, present) + es_spread32(*s.occW, present);
     __syncthreads();
 }
 
 // Once per chain-step (masks + tallies must be current).  Everything is per day or per
-// (day, class): no loop over the employee table.
+// (day, value in use): no loop over the employee table.
 __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int D = K.D;
     const u64 v14 = K.n14 >= 64 ? ~0ull : ((1ull << K.n14) - 1);  // real window starts only
     const u64 v7 = K.n7 >= 64 ? ~0ull : ((1ull << K.n7) - 1);
     const u64 fm = *s.fmask;
-    const int nslot = __popcll(fm);
+    const u64 occT = *s.occT;
+    const unsigned int occW = *s.occW;
     // phase 1: slots (one per first day), their window masks; per-day counts of the day's employee
     for (int d = tid; d < D; d += nt) {
         const int e = s.a[d];
@@ -403,14 +380,15 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
         const int slot = __popcll(fm & ((1ull << f) - 1ull));
         s.dslot[d] = (unsigned char)slot;
         const int t = __popcll(m), w = __popcll(m & K.wkend);
-        s.dayb[ES_DB_TOT + d] = (unsigned char)t;
-        s.dayb[ES_DB_WK + d] = (unsigned char)w;
-        s.dayb[ES_DB_WD + d] = (unsigned char)__popcll(m & s.wdm[d]);
+        s.dayb[d] = (unsigned char)t;
+        s.dayb[s.dp + d] = (unsigned char)w;
+        s.dayb[2 * s.dp + d] = (unsigned char)__popcll(m & s.wdm[d]);
         if (f == d) {
             s.semp[slot] = (uint16_t)e;
             s.smask[slot] = m;
             s.shol[slot] = hol[e];
-            s.skey[slot] = (uint16_t)((t << 5) | w);
+            s.srk[2 * slot] = (unsigned char)__popcll(occT & ((1ull << t) - 1ull));
+            s.srk[2 * slot + 1] = (unsigned char)__popc(occW & ((1u << w) - 1u));
             u64 p14[4], p7[3];
             es_window_planes<14, 4>(m, p14);
             es_window_planes<7, 3>(m, p7);
@@ -421,54 +399,56 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
             q[3] = p7[0] & p7[1] & ~p7[2] & v7;                 // count == 3
         }
     }
-    if (tid == 0) {
-        s.skey[nslot] = 0;  // the class of every absent employee
-        s.misc[ES_NSLOT] = nslot;
+    {   // rank -> value tables of the total / weekend counts in use (j-th set bit)
+        const int j = nt - 1 - tid;  // the last threads: the first ones are busy with first days
+        if (j < ES_TCOLS + ES_WCOLS) {
+            u64 bits = j < ES_TCOLS ? occT : (u64)occW;
+            const int r = j < ES_TCOLS ? j : j - ES_TCOLS;
+            for (int k = 0; k < r; ++k) bits &= bits - 1;
+            s.val[j] = (unsigned char)(bits ? __ffsll((long long)bits) - 1 : 0xff);
+        }
     }
+    if (tid == 0) s.misc[ES_NSLOT] = __popcll(fm);
     __syncthreads();
-    // phase 2: what the day's current employee loses; class representatives
-    for (int d = tid; d < D; d += nt) {
+    // phase 2: what the day's current employee loses, the value of an absent receiver, and the
+    // memo tables.  The soft deltas of a change move depend on the receiving employee only
+    // through its count on the weekday (S2), its total (S3) and its weekend count (S4).
+    for (int d = tid; d < s.dp; d += nt) {
+        if (d >= D) {
+            s.baseW[d] = ES_W_PAD;
+            continue;
+        }
         const int slot = s.dslot[d];
         const u64 m = s.smask[slot];
         const u64* q = s.eq + slot * 4;
         const int lossH = (int)((s.shol[slot] >> d) & 1ull) + __popcll(m & s.part[d]) + __popcll(q[1] & s.cont14[d]);
         const int lossS = __popcll(q[3] & s.cont7[d]);
         s.base[d] = ((unsigned)(0x8000 - lossH) << 16) | (unsigned)(0x8000 - lossS);
-    }
-    for (int c = tid; c <= nslot; c += nt) {
-        const int key = s.skey[c];
-        int r = c;
-        for (int c2 = 0; c2 < c; ++c2)
-            if ((int)s.skey[c2] == key) {
-                r = c2;
-                break;
-            }
-        s.srep[c] = (unsigned char)r;
-    }
-    __syncthreads();
-    // phase 3: memo tables.  The soft S3+S4 delta of a change move depends on the receiving
-    // employee only through its (total, weekend) class, S2 only through its count on the weekday.
-    const int ncol = nslot + 1;
-    for (int k = tid; k < D * ncol; k += nt) {
-        const int d = k / ncol, c = k - d * ncol;
-        if ((int)s.srep[c] != c) continue;
-        const int key = s.skey[c];
-        const int isw = (int)((K.wkend >> d) & 1ull);
-        const int v34 = es_s34_change(s, s.dayb[ES_DB_TOT + d], s.dayb[ES_DB_WK + d], isw, key >> 5, key & 31);
-        s.s34[d * s.ls34 + c] = (signed char)v34;
-        if (c == nslot) {  // an absent employee: no pairs, no window counts, zero days on the weekday
-            const int wd = es_weekday(K, d);
-            const int v2 = wd < 5 ? es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], 0) : 0;
-            s.baseAbs[d] = s.base[d] + (unsigned)(v34 + v2);
-        }
+        // an absent receiver: no pairs, no window counts, zero days anywhere
+        const int to = s.dayb[d], wo = s.dayb[s.dp + d], wd = s.dwd[d];
+        const int isw = wd >= 5 ? 1 : 0;
+        int ds = -lossS + es_s3_delta(s, to, 0) + es_s4_delta(s, to, wo, isw, 0, false);
+        if (wd < 5) ds += es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], 0);
+        s.baseW[d] = ((unsigned)(64 - lossH) << 15) | ((unsigned)(256 + ds) << 6) | (unsigned)d;
     }
     for (int k = tid; k < D * ES_CBINS; k += nt) {
         const int d = k / ES_CBINS, cn = k - d * ES_CBINS;
-        const int wd = es_weekday(K, d);
+        const int wd = s.dwd[d];
         int v = 0;  // only counts some employee actually has on that weekday (and 0) are ever looked up
         if (wd < 5 && cn < ES_CBINS - 1 && (cn == 0 || ((s.occ2[wd] >> cn) & 1u)))
-            v = es_s2_delta(s, wd, (int)s.dayb[ES_DB_WD + d], cn);
+            v = es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], cn);
         s.s2t[k] = (signed char)v;
+    }
+    for (int k = tid; k < D * ES_TCOLS; k += nt) {
+        const int d = k / ES_TCOLS, j = k - d * ES_TCOLS;
+        const int tn = s.val[j];
+        if (tn != 0xff) s.s3t[k] = (signed char)es_s3_delta(s, s.dayb[d], tn);
+    }
+    for (int k = tid; k < D * ES_WCOLS; k += nt) {
+        const int d = k / ES_WCOLS, j = k - d * ES_WCOLS;
+        const int wn = s.val[ES_TCOLS + j];
+        if (wn != 0xff)
+            s.s4t[k] = (signed char)es_s4_delta(s, s.dayb[d], s.dayb[s.dp + d], s.dwd[d] >= 5 ? 1 : 0, wn, true);
     }
     __syncthreads();
 }
@@ -478,6 +458,11 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
 // orders candidates lexicographically by (dhard, dsoft).
 __device__ __forceinline__ int es_v_dh(unsigned int v) { return (int)(v >> 16) - 0x8000; }
 __device__ __forceinline__ int es_v_ds(unsigned int v) { return (int)(v & 0xffffu) - 0x8000; }
+// absent-receiver packing w = (dh + 64) << 15 | (ds + 256) << 6 | day  ->  v
+// (dh in [-21, 1], ds in [-101, 94]: bounded by the window / weekday / spread ranges for D <= 64)
+__device__ __forceinline__ unsigned int es_w_to_v(unsigned int w) {
+    return ((unsigned)(0x8000 - 64 + (int)(w >> 15)) << 16) | (unsigned)(0x8000 - 256 + (int)((w >> 6) & 0x1ffu));
+}
 
 // change: day d goes to the PRESENT employee of `slot` (not the day's current one)
 __device__ __forceinline__ unsigned int es_change_present_v(const EsSmem& s, int d, int slot) {
@@ -487,12 +472,13 @@ __device__ __forceinline__ unsigned int es_change_present_v(const EsSmem& s, int
     const int gs = __popcll(q[2] & s.cont7[d]);
     const int cn = __popcll(m & s.wdm[d]);
     return s.base[d] + ((unsigned)gh << 16) +
-           (unsigned)(gs + (int)s.s2t[d * ES_CBINS + cn] + (int)s.s34[d * s.ls34 + (int)s.srep[slot]]);
+           (unsigned)(gs + (int)s.s2t[d * ES_CBINS + cn] + (int)s.s3t[d * ES_TCOLS + (int)s.srk[2 * slot]] +
+                      (int)s.s4t[d * ES_WCOLS + (int)s.srk[2 * slot + 1]]);
 }
 
 // change: day d goes to an ABSENT employee whose holiday mask is hol
 __device__ __forceinline__ unsigned int es_change_absent_v(const EsSmem& s, int d, u64 hol) {
-    return s.baseAbs[d] + ((unsigned)((hol >> d) & 1ull) << 16);
+    return es_w_to_v(s.baseW[d] + ((unsigned)((hol >> d) & 1ull) << 15));
 }
 
 // swap: days d1 < d2 exchange employees (different).
@@ -516,23 +502,18 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmem& s, const EsConst
     dh += __popcll(q2[0] & only14a) - __popcll(q2[1] & only14b);
     int ds = __popcll(q1[2] & only7b) - __popcll(q1[3] & only7a);
     ds += __popcll(q2[2] & only7a) - __popcll(q2[3] & only7b);
-    const u64 w1 = s.wdm[d1], w2 = s.wdm[d2];
-    if (w1 != w2) {
+    const int wd1 = s.dwd[d1], wd2 = s.dwd[d2];
+    if (wd1 != wd2) {
         // the two weekdays are distinct histograms, so their deltas are independent
-        if (w1) ds += es_s2_delta(s, es_weekday(K, d1), __popcll(m1 & w1), __popcll(m2 & w1));
-        if (w2) ds += es_s2_delta(s, es_weekday(K, d2), __popcll(m2 & w2), __popcll(m1 & w2));
-    }
-    const int k1 = (K.wkend & b1) ? 1 : 0, k2 = (K.wkend & b2) ? 1 : 0;
-    if (k1 != k2) {  // totals (S3) unchanged; weekend counts move between the two employees
-        const int present = s.misc[ES_PRESENT];
-        const int x1 = s.dayb[ES_DB_WK + d1], x2 = s.dayb[ES_DB_WK + d2];
-        EsAdj W;
-        W.add(x1, -1);
-        W.add(x1 - k1 + k2, +1);
-        W.add(x2, -1);
-        W.add(x2 + k1 - k2, +1);
-        const u64 occW = es_occ_after(s.histW, (u64)*s.occW, W);
-        ds += es_spread(occW, present) - es_spread((u64)*s.occW, present);
+        if (wd1 < 5) ds += es_s2_delta(s, wd1, (int)s.dayb[2 * s.dp + d1], __popcll(m2 & s.wdm[d1]));
+        if (wd2 < 5) ds += es_s2_delta(s, wd2, (int)s.dayb[2 * s.dp + d2], __popcll(m1 & s.wdm[d2]));
+        const int k1 = wd1 >= 5 ? 1 : 0, k2 = wd2 >= 5 ? 1 : 0;
+        if (k1 != k2) {  // totals (S3) unchanged; weekend counts move between the two employees
+            const int present = s.misc[ES_PRESENT];
+            const int x1 = s.dayb[s.dp + d1], x2 = s.dayb[s.dp + d2];
+            const unsigned int occ = es_occ_move32(s.histW, *s.occW, x1, x2, x1 - k1 + k2, x2 + k1 - k2);
+            ds += es_spread32(occ, present) - es_spread32(*s.occW, present);
+        }
     }
     return ((unsigned)(0x8000 + dh) << 16) | (unsigned)(0x8000 + ds);
 }
@@ -540,16 +521,6 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmem& s, const EsConst
 // move id: change (d, e) -> d*E + e ; swap (d1<d2) -> D*E + tri(d1,d2)
 __device__ __forceinline__ int es_tri_index(int D, int d1, int d2) {
     return d1 * D - d1 * (d1 + 1) / 2 + (d2 - d1 - 1);
-}
-// inverse of es_tri_index
-__device__ __forceinline__ void es_tri_decode(int D, int r, int& d1, int& d2) {
-    const float b = (float)(2 * D - 1);
-    int x = (int)((b - sqrtf(b * b - 8.0f * (float)r)) * 0.5f);
-    x = max(0, min(x, D - 2));
-    while (x > 0 && x * D - x * (x + 1) / 2 > r) --x;
-    while (x < D - 2 && (x + 1) * D - (x + 1) * (x + 2) / 2 <= r) ++x;
-    d1 = x;
-    d2 = x + 1 + (r - (x * D - x * (x + 1) / 2));
 }
 
 // key = v << 24 | move id  (id < 2^24: 64 days x 65535 employees + swaps)
@@ -563,34 +534,30 @@ __device__ __forceinline__ long long es_block_min(long long key, u64* red) {
         const long long other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other < key ? other : key;
     }
+    if (blockDim.x == 32) return key;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
     __syncthreads();
     if (l == 0) red[w] = (u64)key;
     __syncthreads();
-    if (w == 0) {
-        long long x = (l < nw) ? (long long)red[l] : ES_KEY_INF;
+    long long x = (l < nw) ? (long long)red[l] : ES_KEY_INF;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const long long other = __shfl_xor_sync(0xffffffffu, x, o);
-            x = other < x ? other : x;
-        }
-        if (l == 0) red[32] = (u64)x;
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, x, o);
+        x = other < x ? other : x;
     }
-    __syncthreads();
-    const long long out = (long long)red[32];
-    __syncthreads();
-    return out;
+    return x;
 }
 
 // The neighbourhood scan of one chain-step: every non-identity candidate gets its exact packed
 // (dhard, dsoft); returns this thread's minimum key.  Three passes:
 //   A  change moves to PRESENT employees  (day x slot; full mask arithmetic)
-//   B  change moves to ABSENT employees   (thread per employee, loop over days; the delta is the
-//      per-day table value plus the employee's holiday bit)
+//   B  change moves to ABSENT employees   (thread per employee, loop over days; the value is the
+//      per-day table entry plus the employee's holiday bit, tracked with one min per candidate)
 //   C  swaps
 template <bool DUMP>
 __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol,
-                                             long long* dump_h, long long* dump_s) {
+                                             const uint16_t* __restrict__ tri, long long* dump_h,
+                                             long long* dump_s) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int D = K.D, E = K.E;
     const int nslot = s.misc[ES_NSLOT];
@@ -621,46 +588,44 @@ __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, 
             }
         }
     }
-    // B
-    for (int e = tid; e < E; e += nt) {
-        if (s.mask[e]) continue;
-        const u64 h = hol[e];
-        unsigned int bv = 0xffffffffu;
-        int bd = 0;
-        const unsigned int hlo = (unsigned int)h, hhi = (unsigned int)(h >> 32);
-        const int Dlo = D < 32 ? D : 32;
-#pragma unroll 4
-        for (int d = 0; d < Dlo; ++d) {
-            const unsigned int v = s.baseAbs[d] + (((hlo >> d) & 1u) << 16);
-            if (v < bv) {
-                bv = v;
-                bd = d;
+    {   // B
+        unsigned int bw = 0xffffffffu;
+        int be = 0;
+        const uint4* bw4 = (const uint4*)s.baseW;
+        for (int e = tid; e < E; e += nt) {
+            if (s.mask[e]) continue;
+            const u64 h = hol[e];
+            unsigned int w = 0xffffffffu;
+            for (int d0 = 0; d0 < D; d0 += 4) {
+                const uint4 b = bw4[d0 >> 2];
+                const unsigned int x = (unsigned int)(h >> d0);  // holiday bits of days d0..d0+3
+                const unsigned int w0 = b.x + ((x << 15) & 0x8000u), w1 = b.y + ((x << 14) & 0x8000u);
+                const unsigned int w2 = b.z + ((x << 13) & 0x8000u), w3 = b.w + ((x << 12) & 0x8000u);
+                w = __vimin3_u32(w, w0, w1);
+                w = __vimin3_u32(w, w2, w3);
+                if (DUMP) {
+                    const unsigned int ww[4] = {w0, w1, w2, w3};
+                    for (int j = 0; j < 4 && d0 + j < D; ++j) {
+                        const unsigned int v = es_w_to_v(ww[j]);
+                        dump_h[(d0 + j) * E + e] = es_v_dh(v);
+                        dump_s[(d0 + j) * E + e] = es_v_ds(v);
+                    }
+                }
             }
-            if (DUMP) {
-                dump_h[d * E + e] = es_v_dh(v);
-                dump_s[d * E + e] = es_v_ds(v);
-            }
-        }
-#pragma unroll 4
-        for (int d = 32; d < D; ++d) {
-            const unsigned int v = s.baseAbs[d] + (((hhi >> (d - 32)) & 1u) << 16);
-            if (v < bv) {
-                bv = v;
-                bd = d;
-            }
-            if (DUMP) {
-                dump_h[d * E + e] = es_v_dh(v);
-                dump_s[d * E + e] = es_v_ds(v);
+            if (w < bw) {  // equal value and day: the lower employee index (seen first) stays
+                bw = w;
+                be = e;
             }
         }
-        const long long k2 = es_key(bv, bd * E + e);
-        key = k2 < key ? k2 : key;
+        if (bw != 0xffffffffu) {
+            const long long k2 = es_key(es_w_to_v(bw), (int)(bw & 63u) * E + be);
+            key = k2 < key ? k2 : key;
+        }
     }
     {   // C
         const int n_change = D * E, n_swap = D * (D - 1) / 2;
         for (int r = tid; r < n_swap; r += nt) {
-            int d1, d2;
-            es_tri_decode(D, r, d1, d2);
+            const int dd = tri[r], d1 = dd >> 8, d2 = dd & 0xff;
             const int id = n_change + r;
             if (s.dslot[d1] != s.dslot[d2]) {
                 const unsigned int v = es_swap_v(s, K, d1, d2);
@@ -681,12 +646,17 @@ __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, 
 
 // per-day constants of the handle: part | cont14 | cont7 from the host table, weekday masks
 __device__ __forceinline__ void es_load_consts(const EsSmem& s, const EsConst& K, const u64* __restrict__ dayconst) {
-    for (int k = threadIdx.x; k < 192; k += blockDim.x) s.part[k] = dayconst[k];
-    for (int d = threadIdx.x; d < 64; d += blockDim.x) {
+    for (int d = threadIdx.x; d < s.dp; d += blockDim.x) {
         const int wd = (K.start_wd + d) % 7;
+        s.part[d] = dayconst[d];
+        s.cont14[d] = dayconst[64 + d];
+        s.cont7[d] = dayconst[128 + d];
         s.wdm[d] = (d < K.D && wd < 5) ? K.wd[wd] : 0ull;
+        s.dwd[d] = (unsigned char)wd;
     }
 }
+// (d1 << 8 | d2) of swap r, appended to the day constants by the host
+__device__ __forceinline__ const uint16_t* es_tri_table(const u64* dayconst) { return (const uint16_t*)(dayconst + 192); }
 
 // ------------------------------------------------------------------ the step kernel (K5)
 __global__ void es_step_kernel(EsParams p) {
@@ -696,6 +666,7 @@ __global__ void es_step_kernel(EsParams p) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int D = K.D, E = K.E;
     const int n_change = D * E, n_swap = D * (D - 1) / 2;
+    const uint16_t* tri = es_tri_table(p.dayconst);
     es_load_consts(s, K, p.dayconst);
 
     for (;;) {
@@ -732,8 +703,8 @@ __global__ void es_step_kernel(EsParams p) {
             // non-identity candidates: every (day, employee != current) + every day pair held by
             // two different employees -- each of them is evaluated by es_scan
             scored += (unsigned long long)(n_change - D) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
-            long long key = p.dump_h ? es_scan<true>(s, K, p.hol, p.dump_h, p.dump_s)
-                                     : es_scan<false>(s, K, p.hol, nullptr, nullptr);
+            long long key = p.dump_h ? es_scan<true>(s, K, p.hol, tri, p.dump_h, p.dump_s)
+                                     : es_scan<false>(s, K, p.hol, tri, nullptr, nullptr);
             key = es_block_min(key, s.red);
             if (p.dump_h) break;
             if (key == ES_KEY_INF) {  // empty neighbourhood, local_search.rs:336-338
@@ -755,6 +726,7 @@ __global__ void es_step_kernel(EsParams p) {
             }
             hard += dh;
             soft += ds;
+            __syncthreads();  // every thread has read the tables of this step
             if (tid == 0) {
                 unsigned int kind, x, y;
                 if (id < n_change) {
@@ -767,8 +739,7 @@ __global__ void es_step_kernel(EsParams p) {
                     x = (unsigned)d;
                     y = (unsigned)e;
                 } else {
-                    int d1, d2;
-                    es_tri_decode(D, id - n_change, d1, d2);
+                    const int dd = tri[id - n_change], d1 = dd >> 8, d2 = dd & 0xff;
                     const int e1 = s.a[d1], e2 = s.a[d2];
                     const u64 x2 = (1ull << d1) | (1ull << d2);
                     s.mask[e1] ^= x2;
