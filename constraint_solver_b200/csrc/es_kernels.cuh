@@ -109,12 +109,13 @@ struct EsSmem {
     signed char* s2t;      // [DP][ES_CBINS] S2 delta of giving day d to an employee with cn days on that weekday
     signed char* s3t;      // [DP][ES_TCOLS] S3 delta ... to a present employee whose total has rank j
     signed char* s4t;      // [DP][ES_WCOLS] S4 delta ... to a present employee whose weekend count has rank j
+    signed char* s4s;      // [DP][ES_WCOLS] S4 delta of SWAPPING weekend day d with a weekday of such an employee
     int ns, dp;
 };
 
 struct EsLayout {
     size_t mask, a, hist, occ, occT, fmask, misc, red, day, eq, smask, shol, semp, srk, val, dwd, dslot, dayb, base,
-        baseW, s2t, s3t, s4t, total;
+        baseW, s2t, s3t, s4t, s4s, total;
     int ns, dp;
 };
 __host__ __device__ inline size_t es_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -149,6 +150,7 @@ __host__ __device__ inline EsLayout es_layout(int D, int E) {
     L.s2t = o;     o += dp * ES_CBINS;
     L.s3t = o;     o += dp * ES_TCOLS;
     L.s4t = o;     o += dp * ES_WCOLS;
+    L.s4s = o;     o += dp * ES_WCOLS;
     L.total = es_align(o, 16);
     return L;
 }
@@ -189,6 +191,7 @@ __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     s.s2t = (signed char*)(p + L.s2t);
     s.s3t = (signed char*)(p + L.s3t);
     s.s4t = (signed char*)(p + L.s4t);
+    s.s4s = (signed char*)(p + L.s4s);
     return s;
 }
 
@@ -447,8 +450,14 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
     for (int k = tid; k < D * ES_WCOLS; k += nt) {
         const int d = k / ES_WCOLS, j = k - d * ES_WCOLS;
         const int wn = s.val[ES_TCOLS + j];
-        if (wn != 0xff)
-            s.s4t[k] = (signed char)es_s4_delta(s, s.dayb[d], s.dayb[s.dp + d], s.dwd[d] >= 5 ? 1 : 0, wn, true);
+        if (wn == 0xff) continue;
+        const int isw = s.dwd[d] >= 5 ? 1 : 0, wo = s.dayb[s.dp + d];
+        s.s4t[k] = (signed char)es_s4_delta(s, s.dayb[d], wo, isw, wn, true);
+        if (isw) {  // swap with a weekday of an employee holding wn weekend days: nobody joins or leaves
+            const int present = s.misc[ES_PRESENT];
+            const unsigned int occ = es_occ_move32(s.histW, occW, wo, wn, wo - 1, wn + 1);
+            s.s4s[k] = (signed char)(es_spread32(occ, present) - es_spread32(occW, present));
+        }
     }
     __syncthreads();
 }
@@ -504,16 +513,13 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmem& s, const EsConst
     ds += __popcll(q2[2] & only7a) - __popcll(q2[3] & only7b);
     const int wd1 = s.dwd[d1], wd2 = s.dwd[d2];
     if (wd1 != wd2) {
-        // the two weekdays are distinct histograms, so their deltas are independent
-        if (wd1 < 5) ds += es_s2_delta(s, wd1, (int)s.dayb[2 * s.dp + d1], __popcll(m2 & s.wdm[d1]));
-        if (wd2 < 5) ds += es_s2_delta(s, wd2, (int)s.dayb[2 * s.dp + d2], __popcll(m1 & s.wdm[d2]));
-        const int k1 = wd1 >= 5 ? 1 : 0, k2 = wd2 >= 5 ? 1 : 0;
-        if (k1 != k2) {  // totals (S3) unchanged; weekend counts move between the two employees
-            const int present = s.misc[ES_PRESENT];
-            const int x1 = s.dayb[s.dp + d1], x2 = s.dayb[s.dp + d2];
-            const unsigned int occ = es_occ_move32(s.histW, *s.occW, x1, x2, x1 - k1 + k2, x2 + k1 - k2);
-            ds += es_spread32(occ, present) - es_spread32(*s.occW, present);
-        }
+        // two independent transfers on distinct weekday histograms: day d1 goes e1 -> e2, day d2
+        // goes e2 -> e1; each is the memoised change-move S2 delta for the receiver's count
+        // (weekend rows of s2t are zero)
+        ds += (int)s.s2t[d1 * ES_CBINS + __popcll(m2 & s.wdm[d1])] + (int)s.s2t[d2 * ES_CBINS + __popcll(m1 & s.wdm[d2])];
+        // totals (S3) unchanged; a weekend day and a weekday trade places (S4)
+        if (wd1 >= 5 && wd2 < 5) ds += (int)s.s4s[d1 * ES_WCOLS + (int)s.srk[2 * s2 + 1]];
+        if (wd2 >= 5 && wd1 < 5) ds += (int)s.s4s[d2 * ES_WCOLS + (int)s.srk[2 * s1 + 1]];
     }
     return ((unsigned)(0x8000 + dh) << 16) | (unsigned)(0x8000 + ds);
 }
@@ -659,7 +665,7 @@ __device__ __forceinline__ void es_load_consts(const EsSmem& s, const EsConst& K
 __device__ __forceinline__ const uint16_t* es_tri_table(const u64* dayconst) { return (const uint16_t*)(dayconst + 192); }
 
 // ------------------------------------------------------------------ the step kernel (K5)
-__global__ void es_step_kernel(EsParams p) {
+__global__ void __launch_bounds__(256, 4) es_step_kernel(EsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EsConst& K = p.K;
     const EsSmem s = es_carve(smem_raw, K.D, K.E);
