@@ -348,12 +348,18 @@ __device__ void es_tally(const EsSmem& s, const EsConst& K, const u64* __restric
     __syncthreads();
 }
 
-// Build masks + tallies from a[] and the full score from them.  Block-cooperative.
+// Build masks + tallies from a[] and the full score from them.  Block-cooperative.  The mask
+// table must be all-zero on entry (es_clear_masks after the previous chain).
+__device__ __forceinline__ void es_zero_masks(const EsSmem& s, int E) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) s.mask[e] = 0;
+}
+// clear exactly the entries the current a[] set (<= D stores instead of E)
+__device__ __forceinline__ void es_clear_masks(const EsSmem& s, int D) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s.mask[s.a[d]] = 0;
+}
 __device__ void es_build(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol,
                          int& hard, int& soft) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < K.E; e += nt) s.mask[e] = 0;
-    __syncthreads();
     for (int d = tid; d < K.D; d += nt) atomicOr(&s.mask[s.a[d]], 1ull << d);
     __syncthreads();
     es_tally<true>(s, K, hol);
@@ -674,6 +680,7 @@ __global__ void __launch_bounds__(256, 4) es_step_kernel(EsParams p) {
     const int n_change = D * E, n_swap = D * (D - 1) / 2;
     const uint16_t* tri = es_tri_table(p.dayconst);
     es_load_consts(s, K, p.dayconst);
+    es_zero_masks(s, E);
 
     for (;;) {
         __syncthreads();
@@ -778,6 +785,7 @@ __global__ void __launch_bounds__(256, 4) es_step_kernel(EsParams p) {
             if (it + 1 < p.max_steps) es_tally<false>(s, K, p.hol);  // tallies of the new state
         }
         __syncthreads();
+        es_clear_masks(s, D);  // leave the mask table all-zero for the next chain
         if (p.dump_h) continue;
         for (int k = tid; k < p.stride; k += nt) ga[k] = s.a[k];
         if (tid == 0) {
@@ -798,6 +806,7 @@ __global__ void __launch_bounds__(256, 4) es_step_kernel(EsParams p) {
 __global__ void es_rescore_kernel(EsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EsSmem s = es_carve(smem_raw, p.K.D, p.K.E);
+    es_zero_masks(s, p.K.E);
     for (int local = blockIdx.x; local < p.n_chains; local += gridDim.x) {
         const int chain = p.first_chain + local;
         __syncthreads();
@@ -806,6 +815,7 @@ __global__ void es_rescore_kernel(EsParams p) {
         __syncthreads();
         int hard, soft;
         es_build(s, p.K, p.hol, hard, soft);
+        es_clear_masks(s, p.K.D);
         for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
             p.best_a[(size_t)chain * p.stride + k] = s.a[k];
         if (threadIdx.x == 0) {
@@ -830,6 +840,7 @@ __global__ void es_eval_kernel(EsParams p, int chain, int kind, const uint2* __r
     for (int k = threadIdx.x; k < p.stride; k += blockDim.x)
         s.a[k] = p.a[(size_t)chain * p.stride + k];
     es_load_consts(s, p.K, p.dayconst);
+    es_zero_masks(s, p.K.E);
     __syncthreads();
     int hard, soft;
     es_build(s, p.K, p.hol, hard, soft);
