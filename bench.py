@@ -170,7 +170,8 @@ def run_es(args):
     chains = args.chains if args.chains != 4096 or args.workload == "es2000" else w["chains"]
     threads = os.cpu_count() or 1
     per_chain_moves = D * E + D * (D - 1) // 2
-    if args.impl == "reference":
+    def cpu_sample(steps, warmup):
+        """reference formulation (clone + full re-score per candidate) on a bounded sample"""
         from oracle import oracle as orc
 
         a = orc.es_init(args.seed, 0, D + 1, ids)[:D]
@@ -179,12 +180,17 @@ def run_es(args):
         x = rng.integers(0, D, size=per_step)
         y = rng.integers(0, E, size=per_step)
         times = []
-        for s_ in range(args.warmup + args.steps):
+        for s_ in range(warmup + steps):
             t0 = time.perf_counter()
             orc.es_baseline_sample(a, ids, x, y, orc.ES_CHANGE, threads, 0, hol)
-            if s_ >= args.warmup:
+            if s_ >= warmup:
                 times.append(time.perf_counter() - t0)
-        v = per_step * len(times) / sum(times)
+        return per_step * len(times) / sum(times), times, per_step, a
+
+    if args.impl == "reference":
+        from oracle import oracle as orc
+
+        v, times, per_step, a = cpu_sample(args.steps, args.warmup)
         # time to zero hard violations: one chain, LocalSearch::execute with the full neighbourhood
         t0 = time.perf_counter()
         res = orc.es_local_search(a, ids, 0, hol, allow_no_improvement_for=20,
@@ -239,6 +245,9 @@ def run_es(args):
         eng.step(1)
         if xchg is not None:
             xchg.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -252,7 +261,34 @@ def run_es(args):
         launches += st.kernel_launches
     ev1.record(stream)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    # end to end through the C ABI with HOST buffers (pinned int64 employee ids, the reference's
+    # element type): H2D of the step's input rotas, the step, D2H of every chain's (hard, soft)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((chains, D + 1), dtype=torch.int64, pin_memory=True)
+        host.copy_(torch.from_numpy(np.ascontiguousarray(start_rows)))
+        eng.set_chains_ptr(host.data_ptr(), chains)
+        eng.step(1)
+        barrier()
+        t0 = time.perf_counter()
+        e_moves = 0
+        for _ in range(args.steps):
+            eng.set_chains_ptr(host.data_ptr(), chains)
+            e_moves += eng.step(1).moves_scored
+            eng.scores()
+            if xchg is not None:
+                xchg.sync()
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            te = torch.tensor([dt, float(e_moves)], dtype=torch.float64, device="cuda")
+            a_ = te.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)
+            b_ = te.clone(); dist.all_reduce(b_, op=dist.ReduceOp.SUM)
+            dt, e_moves = float(a_[0]), float(b_[1])
+        e2e = {"value": e_moves / dt, "unit": UNIT, "h2d_bytes_per_step": chains * (D + 1) * 8,
+               "d2h_bytes_per_step": chains * 16 + 64}
     if dist is not None:
         t = torch.tensor([ms, float(moves)], dtype=torch.float64, device="cuda")
         a = t.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
@@ -285,6 +321,22 @@ def run_es(args):
     peak, peak_src = _peaks()
     bpm = (68 * D * E + 128 * (D * (D - 1) // 2)) / per_chain_moves
     ach = moves / args.steps * bpm / (kms / args.steps * 1e-3) / 1e9
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, _, per_step, _ = cpu_sample(3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{per_step} change candidates/step x 3 steps of one D={D} E={E} rota, clone + full "
+                         "re-score each (reference formulation), OpenMP over candidates"}
+    onchip = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", f"r1_ncu_full_es_step_kernel_v4_{args.workload}.json")))
+        onchip = {"issue_slots_pct_of_peak": float(prof["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]),
+                  "alu_pipe_pct_of_peak": float(prof["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"].split()[0]),
+                  "warp_instructions_per_launch": float(prof["smsp__inst_executed.sum"].split()[0]),
+                  "dram_bytes_read_per_launch": prof["dram__bytes_read.sum"],
+                  "source": f"profiles/r1_ncu_full_es_step_kernel_v4_{args.workload}.json"}
+    except Exception:
+        pass
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -295,7 +347,11 @@ def run_es(args):
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "kernel": "es_step_kernel", "peak_source": peak_src,
                      "note": "68 B/change, 128 B/swap algorithmic bytes (SURVEY 8d); state is shared-memory "
-                             "resident, the kernel is integer-issue bound"},
+                             "resident (HBM traffic per launch = the rotas, << 1% of time), so algorithmic GB/s "
+                             "may exceed the HBM peak; the binding resource is the warp-instruction issue rate "
+                             "(onchip, from the committed ncu capture)",
+                     "onchip": onchip},
+        "e2e": e2e, "clocks": clocks, "cpu_baseline": cpu,
         "time_to_zero_hard": {"seconds": ttb, "steps": nsteps, "chains_feasible": int(feasible),
                               "then_local_search_to_stall_s": ls_s,
                               "best_after_ls": [int(st.best_hard), int(st.best_soft)],

@@ -201,6 +201,8 @@ void nq_free(cs_nq_handle* h) {
     cudaFree(h->d_ls_rng);
     if (h->is_big) {
         cudaFree(h->big.rows);
+        cudaFree(h->big.Q);
+        cudaFree(h->big.cb);
         cudaFree(h->big.c);
         cudaFree(h->big.R);
         cudaFree(h->big.D1);

@@ -35,9 +35,19 @@ struct NqBig {
     long long* key;                   // [1] packed (v, i, j) of this partition / after reduce
     int i_begin, i_end;               // this partition's column range
     long long* dump;
+    // packed-window fast scan (nqb_scan_packed_kernel): byte counters, 4 byte-shifted copies of
+    // each diagonal array (copy c, byte y = D[y + c]; Q2's copies follow Q1's), rebuilt per step
+    unsigned char* Q;                 // [8][ldb]
+    unsigned char* cb;                // [n_pad + 128] own-lines sum per column as a byte
+    unsigned int* maxcount;           // [1] largest diagonal line count (set by nqb_pack_kernel)
+    int ldb;
+    int use_packed;                   // host: permutation board, n >= NQBP_MIN_N, not forced scalar
 };
 
-__host__ __device__ inline int nqb_ld(int n_pad) { return 2 * n_pad + 128; }
+constexpr int NQBP_MIN_N = 256;
+constexpr int NQBP_MAX_COUNT = 62;   // four byte counters + slack stay below 256 (as nq_packed.cuh)
+__host__ __device__ inline int nqb_ldb(int n_pad) { return (2 * n_pad + 256 + 15) & ~15; }
+__host__ __device__ inline int nqb_ld(int n_pad) { return nqb_ldb(n_pad) + 64; }
 
 __global__ void nqb_zero_kernel(NqBig b) {
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -96,9 +106,12 @@ __global__ void nqb_compute_c_kernel(NqBig b) {
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
          j += (long long)gridDim.x * blockDim.x) {
         const int r = (int)b.rows[j];
-        b.c[j] = b.D1[j - r + n - 1] + b.D2[j + r];
+        const unsigned int cj = b.D1[j - r + n - 1] + b.D2[j + r];
+        b.c[j] = cj;
+        b.cb[j] = (unsigned char)(cj < 255u ? cj : 255u);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *b.maxcount = 0;
         *b.tile_counter = 0;
         *b.key1 = ~0ull;
         *b.jmin = 0xffffffffu;
@@ -123,6 +136,7 @@ __device__ __forceinline__ int nqb_swap_half(const NqBig& b, int i, int j) {
 template <bool PERM, bool DUMP>
 __global__ void __launch_bounds__(256) nqb_scan_kernel(NqBig b) {
     constexpr int TI = NQB_TI;
+    if (PERM && b.use_packed && *b.maxcount <= (unsigned)NQBP_MAX_COUNT) return;  // the packed scan runs instead
     const int n = b.n, lane = threadIdx.x & 31;
     const unsigned int* __restrict__ rows = b.rows;
     const unsigned int* __restrict__ cc = b.c;
@@ -206,6 +220,202 @@ __global__ void __launch_bounds__(256) nqb_scan_kernel(NqBig b) {
         atomicMin(b.key1, ((unsigned long long)(wv + NQB_BIAS) << 32) | wi2);
     if (!PERM) ident = __reduce_add_sync(0xffffffffu, ident);
     if (lane == 0 && pairs) atomicAdd(b.scored, pairs - ident);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Packed-window scan for big boards: the shared-memory fast scan of nq_packed.cuh with the byte
+// counters in global memory (L2-resident, gathers served by L1).  A CTA takes 128 consecutive
+// columns (8 warps x 16 column slots) so its warps sweep the same j chunks together and their
+// adjacent 16-byte gather windows share L1 sectors; a lane owns 4 consecutive columns j.
+// Diagonal ids need 21 bits at n = 10^6, so the 16x2 attack test compares a low and a high half.
+// Identical integer value per move as nqb_scan_kernel (parity: cs_nq_neighbourhood_deltas runs
+// THIS scan with the dump flag whenever the board qualifies).
+
+// u32 counters -> the four byte-shifted copies of both arrays, and the largest line count
+__global__ void nqb_pack_kernel(NqBig b) {
+    const int ldb = b.ldb;
+    unsigned int mx = 0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ldb / 4;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(4 * k);
+#pragma unroll
+        for (int arr = 0; arr < 2; ++arr) {
+            const unsigned int* __restrict__ D = arr ? b.D2 : b.D1;
+            unsigned int d[7];
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                d[t] = (y + t < b.ld) ? D[y + t] : 0u;
+                mx = max(mx, d[t]);
+                d[t] &= 0xffu;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *(unsigned int*)(b.Q + (size_t)(4 * arr + c) * ldb + y) =
+                    d[c] | (d[c + 1] << 8) | (d[c + 2] << 16) | (d[c + 3] << 24);
+        }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(b.maxcount, mx);
+}
+
+#ifndef NQBP_TI_VALUE
+#define NQBP_TI_VALUE 8
+#endif
+constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = 8 * NQBP_TI;  // 8 warps x TI slots
+constexpr int NQBP_INF16 = 0x3fff, NQBP_BIAS = 128;
+
+template <bool DUMP>
+__global__ void __launch_bounds__(256, 2) nqb_scan_packed_kernel(NqBig b) {
+    if (*b.maxcount > (unsigned)NQBP_MAX_COUNT) return;  // a line too long for byte sums: nqb_scan_kernel runs
+    constexpr int TI = NQBP_TI;
+    __shared__ int s_group;
+    const int n = b.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned char* __restrict__ Q = b.Q;
+    const unsigned int* __restrict__ rows = b.rows;
+    const unsigned char* __restrict__ cb = b.cb;
+    const int ldbm1 = b.ldb - 1, q2off = 4 * b.ldb;
+    const int g_first = b.i_begin / NQBP_GROUP;
+    const int g_count = b.i_end > b.i_begin ? (b.i_end + NQBP_GROUP - 1) / NQBP_GROUP - g_first : 0;
+    int best_v = NQ_INF;
+    unsigned int best_i = 0xffffffffu;
+    unsigned long long pairs = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_group = (int)atomicAdd(b.tile_counter, 1u);
+        __syncthreads();
+        const int g = s_group;
+        if (g >= g_count) break;
+        const int i0 = (g_first + g) * NQBP_GROUP + w * TI;
+        if (i0 >= b.i_end || i0 + TI <= b.i_begin || i0 >= n - 1) continue;
+        const int jbase = i0 & ~(NQBP_CHUNK - 1);
+
+        int pv1[TI], pv2[TI];
+        unsigned NUl[TI / 2], NUh[TI / 2], NWl[TI / 2], NWh[TI / 2], m[TI / 2];
+#pragma unroll
+        for (int p = 0; p < TI / 2; ++p) {
+            unsigned ul = 0, uh = 0, wl = 0, wh = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int a = 2 * p + h, i = i0 + a;
+                const int ri = (int)__ldg(rows + i);  // rows are zero-padded past n (slots masked later)
+                const int x1 = n - 1 - ri, x2 = ri;
+                // copy (x & 3), word (x & ~3):  (x & 3) * ldb + (x & ~3) == x + (x & 3) * (ldb - 1)
+                pv1[a] = x1 + (x1 & 3) * ldbm1 + 4 * lane + jbase;
+                pv2[a] = q2off + x2 + (x2 & 3) * ldbm1 + 4 * lane + jbase;
+                const int idu = ri - i + n, idw = ri + i;  // diagonal ids, 0 <= id < 2^21 for real columns
+                ul |= (unsigned)((2 * (idu & 0x7fff)) & 0xffff) << (16 * h);
+                uh |= (unsigned)((2 * ((idu >> 15) & 0x7fff)) & 0xffff) << (16 * h);
+                wl |= (unsigned)((2 * (idw & 0x7fff)) & 0xffff) << (16 * h);
+                wh |= (unsigned)((2 * ((idw >> 15) & 0x7fff)) & 0xffff) << (16 * h);
+                if (lane == 0 && i >= b.i_begin && i < b.i_end && i < n - 1) pairs += (unsigned long long)(n - 1 - i);
+            }
+            NUl[p] = ~ul;  // x ^ ~y == ~(x ^ y): equal halves give 0xFFFF
+            NUh[p] = ~uh;
+            NWl[p] = ~wl;
+            NWh[p] = ~wh;
+            m[p] = (unsigned)NQBP_INF16 * 0x10001u;
+        }
+        const int A1 = i0 + n - 1, A2 = i0;
+
+        auto chunk = [&](int dj, bool masked) {
+            const int j0 = jbase + dj + NQBP_TJ * lane;
+            const uint4 r4 = __ldg((const uint4*)(rows + j0));
+            const unsigned c4 = __ldg((const unsigned*)(cb + j0));
+            // lane-consecutive windows: T[a] = D1[j0..j0+3 - r_ia] + D2[j0..j0+3 + r_ia] (streamed once)
+            unsigned T[TI];
+#pragma unroll
+            for (int a = 0; a < TI; ++a)
+                T[a] = __ldcs((const unsigned*)(Q + pv1[a] + dj)) + __ldcs((const unsigned*)(Q + pv2[a] + dj));
+            unsigned TP[NQBP_TJ][TI / 4];  // byte transpose: TP[b][g] = slots 4g..4g+3 at j_b
+#pragma unroll
+            for (int g4 = 0; g4 < TI / 4; ++g4) {
+                const unsigned x0 = __byte_perm(T[4 * g4 + 0], T[4 * g4 + 1], 0x5140);
+                const unsigned x1 = __byte_perm(T[4 * g4 + 2], T[4 * g4 + 3], 0x5140);
+                const unsigned y0 = __byte_perm(T[4 * g4 + 0], T[4 * g4 + 1], 0x7362);
+                const unsigned y1 = __byte_perm(T[4 * g4 + 2], T[4 * g4 + 3], 0x7362);
+                TP[0][g4] = __byte_perm(x0, x1, 0x5410);
+                TP[1][g4] = __byte_perm(x0, x1, 0x7632);
+                TP[2][g4] = __byte_perm(y0, y1, 0x5410);
+                TP[3][g4] = __byte_perm(y0, y1, 0x7632);
+            }
+#pragma unroll
+            for (int bb = 0; bb < NQBP_TJ; ++bb) {
+                const int j = j0 + bb;
+                const int rj = (int)(bb == 0 ? r4.x : bb == 1 ? r4.y : bb == 2 ? r4.z : r4.w);
+                const int cj = (int)(c4 >> (8 * bb)) & 0xff;
+                // data-dependent windows over the 16 column slots (shared with the neighbouring warps)
+                const int t1 = A1 - rj, t2 = A2 + rj;
+                const unsigned char* g1 = Q + t1 + (t1 & 3) * ldbm1;
+                const unsigned char* g2 = Q + q2off + t2 + (t2 & 3) * ldbm1;
+                unsigned X[TI / 4];
+#pragma unroll
+                for (int g4 = 0; g4 < TI / 4; ++g4)
+                    X[g4] = __ldg((const unsigned*)(g1 + 4 * g4)) + __ldg((const unsigned*)(g2 + 4 * g4)) + TP[bb][g4];
+                const unsigned kj = (unsigned)(7 + NQBP_BIAS - cj) * 0x10001u;
+                const int idu = rj - j + n, idw = rj + j;
+                const unsigned ul = (unsigned)(2 * (idu & 0x7fff)) * 0x10001u;
+                const unsigned uh = (unsigned)(2 * ((idu >> 15) & 0x7fff)) * 0x10001u;
+                const unsigned wl = (unsigned)(2 * (idw & 0x7fff)) * 0x10001u;
+                const unsigned wh = (unsigned)(2 * ((idw >> 15) & 0x7fff)) * 0x10001u;
+#pragma unroll
+                for (int p = 0; p < TI / 2; ++p) {
+                    const unsigned x16 = __byte_perm(X[p / 2], 0u, (p & 1) ? 0x4342 : 0x4140);
+                    unsigned y = x16 + kj;
+                    // same diagonal <=> low and high id halves both equal: XNORs all ones (-1), else <= 0xFFFD (-3)
+                    const unsigned eu = (ul ^ NUl[p]) & (uh ^ NUh[p]);
+                    const unsigned ew = (wl ^ NWl[p]) & (wh ^ NWh[p]);
+                    const unsigned a2 = __vimax3_u16x2(eu, ew, 0xFFFDFFFDu);
+                    if (masked) {
+                        const int ia = i0 + 2 * p;
+                        unsigned pen = 0;
+                        if (!(j > ia && j < n)) pen |= 0x00004000u;
+                        if (!(j > ia + 1 && j < n)) pen |= 0x40000000u;
+                        y = __vadd2(y, pen);
+                    }
+                    if (DUMP) {
+                        const unsigned z = __vadd2(y, a2);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = i0 + 2 * p + h;
+                            if (j > i && j < n && i >= b.i_begin && i < b.i_end) {
+                                const int zz = (int)(short)((z >> (16 * h)) & 0xffff);
+                                b.dump[nq_swap_index(n, i, j)] = 2ll * (long long)(zz - NQBP_BIAS - (int)cb[i]);
+                            }
+                        }
+                    }
+                    m[p] = __viaddmin_s16x2(y, a2, m[p]);
+                }
+            }
+        };
+
+        chunk(0, true);  // the chunk holding the tile: needs the j > i mask
+        const int dj_full = (n & ~(NQBP_CHUNK - 1)) - jbase;  // end of the full chunks
+        int dj = NQBP_CHUNK;
+        for (; dj < dj_full; dj += NQBP_CHUNK) chunk(dj, false);
+        if (jbase + dj < n) chunk(dj, true);
+
+#pragma unroll
+        for (int p = 0; p < TI / 2; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + 2 * p + h;
+                const int mv = (int)(short)((m[p] >> (16 * h)) & 0xffff);
+                if (i < n - 1 && i >= b.i_begin && i < b.i_end && mv < NQBP_INF16 / 2) {
+                    const int v = mv - NQBP_BIAS - (int)cb[i];
+                    if (v < best_v || (v == best_v && (unsigned)i < best_i)) {
+                        best_v = v;
+                        best_i = (unsigned)i;
+                    }
+                }
+            }
+    }
+    const int wv = __reduce_min_sync(0xffffffffu, best_v);
+    const unsigned wi2 = __reduce_min_sync(0xffffffffu, best_v == wv ? best_i : 0xffffffffu);
+    if (lane == 0 && wv < NQ_INF)
+        atomicMin(b.key1, ((unsigned long long)(wv + NQB_BIAS) << 32) | wi2);
+    if (lane == 0 && pairs) atomicAdd(b.scored, pairs);
 }
 
 // lowest partner j of the winning column that attains the minimum

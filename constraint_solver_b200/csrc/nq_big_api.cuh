@@ -51,13 +51,18 @@ void nqb_alloc(cs_nq_handle* h) {
     b.n = (int)h->cfg.n;
     b.n_pad = h->n_pad;
     b.ld = nqb_ld(h->n_pad);
-    CU(cudaMalloc(&b.rows, (size_t)b.n_pad * 4));
+    CU(cudaMalloc(&b.rows, (size_t)(b.n_pad + 128) * 4));  // zero slack: the packed scan reads whole chunks
     CU(cudaMalloc(&b.c, (size_t)b.n_pad * 4));
+    b.ldb = nqb_ldb(h->n_pad);
+    CU(cudaMalloc(&b.Q, (size_t)8 * b.ldb));
+    CU(cudaMalloc(&b.cb, (size_t)b.n_pad + 128));
+    CU(cudaMemset(b.cb, 0, (size_t)b.n_pad + 128));
+    b.use_packed = 0;
     CU(cudaMalloc(&b.R, (size_t)b.n_pad * 4));
     CU(cudaMalloc(&b.D1, (size_t)b.ld * 4));
     CU(cudaMalloc(&b.D2, (size_t)b.ld * 4));
     CU(cudaMalloc(&h->d_best_rows32, (size_t)b.n_pad * 4));
-    // one block of scalars: score, ident_pairs, key1, scored, key | tile_counter, jmin
+    // one block of scalars: score, ident_pairs, key1, scored, key | tile_counter, jmin, maxcount
     long long* sc = nullptr;
     CU(cudaMalloc(&sc, 8 * sizeof(long long)));
     CU(cudaMemset(sc, 0, 8 * sizeof(long long)));
@@ -68,12 +73,13 @@ void nqb_alloc(cs_nq_handle* h) {
     b.key = sc + 4;
     b.tile_counter = (unsigned int*)(sc + 5);
     b.jmin = (unsigned int*)(sc + 6);
+    b.maxcount = (unsigned int*)(sc + 7);
     b.dump = nullptr;
     CU(cudaMalloc(&h->d_bstep, sizeof(NqBigStep)));
     CU(cudaMallocHost(&h->h_bstep, sizeof(NqBigStep)));
     CU(cudaMallocHost(&h->h_key, sizeof(long long)));
     CU(cudaMallocHost(&h->h_scored, sizeof(unsigned long long)));
-    CU(cudaMemset(b.rows, 0, (size_t)b.n_pad * 4));
+    CU(cudaMemset(b.rows, 0, (size_t)(b.n_pad + 128) * 4));
     CU(cudaMemset(h->d_best_rows32, 0, (size_t)b.n_pad * 4));
     nqb_set_range(h);
 }
@@ -103,7 +109,15 @@ bool nqb_is_perm(cs_nq_handle* h) {
 void nqb_enqueue_scan(cs_nq_handle* h, bool perm, long long* dump) {
     NqBig b = h->big;
     b.dump = dump;
+    b.use_packed = (perm && b.n >= NQBP_MIN_N && !(h->cfg.flags & CS_NQ_FLAG_SCALAR)) ? 1 : 0;
     nqb_compute_c_kernel<<<nqb_grid(h, b.n), 256, 0, h->stream>>>(b);
+    if (b.use_packed) {  // byte copies + largest line count, then the packed scan (no-op if a line is too long)
+        nqb_pack_kernel<<<nqb_grid(h, b.ldb / 4), 256, 0, h->stream>>>(b);
+        if (dump) nqb_scan_packed_kernel<true><<<h->sm_count * 2, 256, 0, h->stream>>>(b);
+        else nqb_scan_packed_kernel<false><<<h->sm_count * 2, 256, 0, h->stream>>>(b);
+        // the fallback below returns at once unless the packed scan declined; it needs a fresh tile counter
+        CU(cudaMemsetAsync(b.tile_counter, 0, sizeof(unsigned int), h->stream));
+    }
     const int grid = h->sm_count * 4;
     if (perm) {
         if (dump) nqb_scan_kernel<true, true><<<grid, 256, 0, h->stream>>>(b);

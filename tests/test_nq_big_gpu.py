@@ -168,3 +168,90 @@ def test_million_queens_partition_properties():
         with cs.NQueensChains(n, 1) as f:  # fresh rebuild of the counters from the new rows
             f.set_chains(rows1)
             assert int(f.scores()[0]) == s0 + 2 * v
+
+
+def test_packed_global_scan_equals_oracle_and_scalar_scan():
+    """nqb_scan_packed_kernel (byte counters in global memory, 16x2 SIMD, hi/lo diagonal ids) runs
+    for permutation boards with n >= 256: every candidate delta == the oracle's full re-score
+    difference, and the trajectory equals the scalar global scan (CS_NQ_FLAG_SCALAR) and the
+    shared-memory path."""
+    rng = np.random.default_rng(11)
+    for n in (256, 257, 300, 383, 384, 500, 641):
+        rows = np.ascontiguousarray(rng.permutation(n), dtype=np.int64)
+        with cs.NQueensChains(n, 1, force_global=True) as e:
+            e.set_chains(rows)
+            dev = e.neighbourhood_deltas(0)
+        ref = orc.nq_neighbourhood_deltas(rows, orc.SWAP)
+        bad = np.nonzero(dev != ref)[0]
+        assert bad.size == 0, (n, bad[:5], dev[bad[:5]], ref[bad[:5]])
+    # many attacking pairs: the identity permutation puts n queens on one diagonal -> a line
+    # longer than 62 -> the packed scan must decline and the scalar scan must answer
+    for rows in (np.arange(300, dtype=np.int64), np.arange(300, dtype=np.int64)[::-1].copy()):
+        with cs.NQueensChains(300, 1, force_global=True) as e:
+            e.set_chains(rows)
+            assert np.array_equal(e.neighbourhood_deltas(0), orc.nq_neighbourhood_deltas(rows, orc.SWAP))
+    # a board with long-but-legal lines (blocks of 40 on one diagonal) stays on the packed scan
+    n = 400
+    rows = np.arange(n, dtype=np.int64)
+    for s in range(0, n, 40):
+        rows[s:s + 40] = (rows[s:s + 40] + 7 * (s // 40)) % n
+    if len(set(rows.tolist())) == n:
+        with cs.NQueensChains(n, 1, force_global=True) as e:
+            e.set_chains(rows)
+            assert np.array_equal(e.neighbourhood_deltas(0), orc.nq_neighbourhood_deltas(rows, orc.SWAP))
+    for n, seed in [(300, 1), (1000, 2), (4000, 3)]:
+        start = orc.nq_init_perm(seed, 0, n)
+        with cs.NQueensChains(n, 1, trace_capacity=16, force_global=True) as a, \
+                cs.NQueensChains(n, 1, trace_capacity=16, force_global=True, force_scalar=True) as b, \
+                cs.NQueensChains(n, 1, trace_capacity=16) as c:
+            for e in (a, b, c):
+                e.set_chains(start)
+            sa, sb, sc = a.step(6), b.step(6), c.step(6)
+            ma, ca, ta = a.trace(0)
+            for e, st in ((b, sb), (c, sc)):
+                m2, c2, t2 = e.trace(0)
+                assert ta == t2 and np.array_equal(ma, m2) and np.array_equal(ca, c2)
+                assert st.moves_scored == sa.moves_scored and st.best_score == sa.best_score
+            r = start.copy()
+            for (i, j), s in zip(ma, ca):  # replay through the oracle scorer
+                r[i], r[j] = r[j], r[i]
+                assert orc.nq_score(r) == int(s)
+
+
+def test_packed_global_scan_partitions():
+    """5 partitions of a permutation board (packed scan per slice): min of the keys applied on
+    every replica == the unpartitioned step; the slices cover the neighbourhood exactly once."""
+    import torch
+    from constraint_solver_b200.dist import device_view
+
+    n, parts = 3000, 5
+    start = orc.nq_init_perm(9, 0, n)
+    with cs.NQueensChains(n, 1, trace_capacity=4, force_global=True) as whole:
+        whole.set_chains(start)
+        whole.step(2)
+        wmv, wsc, _ = whole.trace(0)
+        want = whole.get_chains()[0]
+    engines = [cs.NQueensChains(n, 1, trace_capacity=4, force_global=True) for _ in range(parts)]
+    try:
+        views = []
+        for k, e in enumerate(engines):
+            e.set_chains(start)
+            e.set_partition(k, parts)
+            views.append(device_view(e.part_key_device_ptr(), (1,), "<i8", torch.device("cuda", 0)))
+        for step in range(2):
+            for e in engines:
+                e.part_scan()
+            torch.cuda.synchronize()
+            best = min(int(v.item()) for v in views)
+            for v in views:
+                v.fill_(best)
+            torch.cuda.synchronize()
+            moves = sum(e.part_apply().moves_scored for e in engines)
+            assert moves == n * (n - 1) // 2
+        for e in engines:
+            mv, sc, _ = e.trace(0)
+            assert np.array_equal(mv, wmv) and np.array_equal(sc, wsc)
+            assert np.array_equal(e.get_chains()[0], want)
+    finally:
+        for e in engines:
+            e.close()
