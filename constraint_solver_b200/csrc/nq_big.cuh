@@ -35,9 +35,9 @@ struct NqBig {
     long long* key;                   // [1] packed (v, i, j) of this partition / after reduce
     int i_begin, i_end;               // this partition's column range
     long long* dump;
-    // packed-window fast scan (nqb_scan_packed_kernel): byte counters, 4 byte-shifted copies of
+    // packed-window fast scan (nqb_scan_packed_kernel): byte counters, 8 byte-shifted copies of
     // each diagonal array (copy c, byte y = D[y + c]; Q2's copies follow Q1's), rebuilt per step
-    unsigned char* Q;                 // [8][ldb]
+    unsigned char* Q;                 // [16][ldb]
     unsigned char* cb;                // [n_pad + 128] own-lines sum per column as a byte
     unsigned int* maxcount;           // [1] largest diagonal line count (set by nqb_pack_kernel)
     int ldb;
@@ -45,6 +45,7 @@ struct NqBig {
 };
 
 constexpr int NQBP_MIN_N = 256;
+constexpr int NQBP_COPIES = 8;      // byte shifts 0..7: any 8-counter window is one aligned 64-bit word
 constexpr int NQBP_MAX_COUNT = 62;   // four byte counters + slack stay below 256 (as nq_packed.cuh)
 __host__ __device__ inline int nqb_ldb(int n_pad) { return (2 * n_pad + 256 + 15) & ~15; }
 __host__ __device__ inline int nqb_ld(int n_pad) { return nqb_ldb(n_pad) + 64; }
@@ -232,27 +233,30 @@ __global__ void __launch_bounds__(256) nqb_scan_kernel(NqBig b) {
 // Identical integer value per move as nqb_scan_kernel (parity: cs_nq_neighbourhood_deltas runs
 // THIS scan with the dump flag whenever the board qualifies).
 
-// u32 counters -> the four byte-shifted copies of both arrays, and the largest line count
+// u32 counters -> the eight byte-shifted copies of both arrays, and the largest line count
 __global__ void nqb_pack_kernel(NqBig b) {
     const int ldb = b.ldb;
     unsigned int mx = 0;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ldb / 4;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ldb / 8;
          k += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(4 * k);
+        const int y = (int)(8 * k);
 #pragma unroll
         for (int arr = 0; arr < 2; ++arr) {
             const unsigned int* __restrict__ D = arr ? b.D2 : b.D1;
-            unsigned int d[7];
+            unsigned int d[15];
 #pragma unroll
-            for (int t = 0; t < 7; ++t) {
+            for (int t = 0; t < 15; ++t) {
                 d[t] = (y + t < b.ld) ? D[y + t] : 0u;
                 mx = max(mx, d[t]);
                 d[t] &= 0xffu;
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                *(unsigned int*)(b.Q + (size_t)(4 * arr + c) * ldb + y) =
-                    d[c] | (d[c + 1] << 8) | (d[c + 2] << 16) | (d[c + 3] << 24);
+            for (int c = 0; c < NQBP_COPIES; ++c) {
+                uint2 v;
+                v.x = d[c] | (d[c + 1] << 8) | (d[c + 2] << 16) | (d[c + 3] << 24);
+                v.y = d[c + 4] | (d[c + 5] << 8) | (d[c + 6] << 16) | (d[c + 7] << 24);
+                *(uint2*)(b.Q + (size_t)(NQBP_COPIES * arr + c) * ldb + y) = v;
+            }
         }
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(256, 2) nqb_scan_packed_kernel(NqBig b) {
     const unsigned char* __restrict__ Q = b.Q;
     const unsigned int* __restrict__ rows = b.rows;
     const unsigned char* __restrict__ cb = b.cb;
-    const int ldbm1 = b.ldb - 1, q2off = 4 * b.ldb;
+    const int ldbm1 = b.ldb - 1, q2off = NQBP_COPIES * b.ldb;
     const int g_first = b.i_begin / NQBP_GROUP;
     const int g_count = b.i_end > b.i_begin ? (b.i_end + NQBP_GROUP - 1) / NQBP_GROUP - g_first : 0;
     int best_v = NQ_INF;
@@ -347,12 +351,16 @@ __global__ void __launch_bounds__(256, 2) nqb_scan_packed_kernel(NqBig b) {
                 const int cj = (int)(c4 >> (8 * bb)) & 0xff;
                 // data-dependent windows over the 16 column slots (shared with the neighbouring warps)
                 const int t1 = A1 - rj, t2 = A2 + rj;
-                const unsigned char* g1 = Q + t1 + (t1 & 3) * ldbm1;
-                const unsigned char* g2 = Q + q2off + t2 + (t2 & 3) * ldbm1;
+                // copy (t & 7), 64-bit word (t & ~7): one sector per load
+                const unsigned char* g1 = Q + t1 + (t1 & 7) * ldbm1;
+                const unsigned char* g2 = Q + q2off + t2 + (t2 & 7) * ldbm1;
                 unsigned X[TI / 4];
 #pragma unroll
-                for (int g4 = 0; g4 < TI / 4; ++g4)
-                    X[g4] = __ldg((const unsigned*)(g1 + 4 * g4)) + __ldg((const unsigned*)(g2 + 4 * g4)) + TP[bb][g4];
+                for (int g8 = 0; g8 < TI / 8; ++g8) {
+                    const uint2 v1 = __ldg((const uint2*)(g1 + 8 * g8)), v2 = __ldg((const uint2*)(g2 + 8 * g8));
+                    X[2 * g8] = v1.x + v2.x + TP[bb][2 * g8];
+                    X[2 * g8 + 1] = v1.y + v2.y + TP[bb][2 * g8 + 1];
+                }
                 const unsigned kj = (unsigned)(7 + NQBP_BIAS - cj) * 0x10001u;
                 const int idu = rj - j + n, idw = rj + j;
                 const unsigned ul = (unsigned)(2 * (idu & 0x7fff)) * 0x10001u;

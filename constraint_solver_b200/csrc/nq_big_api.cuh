@@ -54,7 +54,7 @@ void nqb_alloc(cs_nq_handle* h) {
     CU(cudaMalloc(&b.rows, (size_t)(b.n_pad + 128) * 4));  // zero slack: the packed scan reads whole chunks
     CU(cudaMalloc(&b.c, (size_t)b.n_pad * 4));
     b.ldb = nqb_ldb(h->n_pad);
-    CU(cudaMalloc(&b.Q, (size_t)8 * b.ldb));
+    CU(cudaMalloc(&b.Q, (size_t)2 * NQBP_COPIES * b.ldb));
     CU(cudaMalloc(&b.cb, (size_t)b.n_pad + 128));
     CU(cudaMemset(b.cb, 0, (size_t)b.n_pad + 128));
     b.use_packed = 0;
@@ -112,7 +112,7 @@ void nqb_enqueue_scan(cs_nq_handle* h, bool perm, long long* dump) {
     b.use_packed = (perm && b.n >= NQBP_MIN_N && !(h->cfg.flags & CS_NQ_FLAG_SCALAR)) ? 1 : 0;
     nqb_compute_c_kernel<<<nqb_grid(h, b.n), 256, 0, h->stream>>>(b);
     if (b.use_packed) {  // byte copies + largest line count, then the packed scan (no-op if a line is too long)
-        nqb_pack_kernel<<<nqb_grid(h, b.ldb / 4), 256, 0, h->stream>>>(b);
+        nqb_pack_kernel<<<nqb_grid(h, b.ldb / 8), 256, 0, h->stream>>>(b);
         if (dump) nqb_scan_packed_kernel<true><<<h->sm_count * 2, 256, 0, h->stream>>>(b);
         else nqb_scan_packed_kernel<false><<<h->sm_count * 2, 256, 0, h->stream>>>(b);
         // the fallback below returns at once unless the packed scan declined; it needs a fresh tile counter
