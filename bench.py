@@ -393,8 +393,12 @@ def run_nq1m(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    start_rows = eng.get_chains() if not args.no_e2e else None
     for _ in range(args.warmup):
         board.step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -406,7 +410,29 @@ def run_nq1m(args):
         score = st.best_score
     ev1.record(stream)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    # end to end: the board arrives in HOST memory (pinned int64 rows, the reference's element
+    # type), is uploaded + counted, one partitioned step runs, the new score is read back
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((1, n), dtype=torch.int64, pin_memory=True)
+        host.copy_(torch.from_numpy(start_rows))
+        barrier()
+        t0 = time.perf_counter()
+        e_moves = 0
+        for _ in range(args.steps):
+            eng.set_chains_ptr(host.data_ptr(), 1)
+            e_moves += board.step().moves_scored
+            eng.scores()
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt, float(e_moves)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            a_ = te.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)
+            b_ = te.clone(); dist.all_reduce(b_, op=dist.ReduceOp.SUM)
+            dt, e_moves = float(a_[0]), float(b_[1])
+        e2e = {"value": e_moves / dt, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": 8 + 48}
     t = torch.tensor([ms, float(moves)], dtype=torch.float64, device="cuda")
     if dist is not None:
         a = t.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
@@ -426,9 +452,19 @@ def run_nq1m(args):
                                    f"({n * (n - 1) // 2} candidates/step) partitioned x{world}, "
                                    "8-byte min-allreduce per step, replicas apply the same move"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "kernel": "nqb_scan_kernel",
+                         "frac": ach / peak, "traffic": _nqb_traffic(), "kernel": "nqb_scan_packed_kernel",
                          "peak_source": peak_src,
-                         "note": "24 MB state is L2-resident; 40 B/move algorithmic (u32), per GPU"},
+                         "note": "state (rows + byte-counter copies, 40 MB at n=1e6) is L2-resident: DRAM traffic "
+                                 "per launch is a few MB, so 40 B/move algorithmic (u32, SURVEY 8d) exceeds the "
+                                 "HBM peak; the binding resources are the L1 sector rate and L2 latency (onchip, "
+                                 "from the committed ncu capture)",
+                         "onchip": _nqb_onchip()},
+            "e2e": e2e, "clocks": clocks,
+            "cpu_baseline": None if args.no_cpu_baseline else {
+                "value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": "none: ONE candidate of the reference formulation (clone + full O(n^2) re-score) at "
+                          "n=1e6 is 5e11 pair tests (minutes of CPU time), so no bounded sample of this workload "
+                          "exists; see the default workload (n=10000) for the measured CPU figure"},
             "score_after": score, "gpu_launches": launches}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -663,6 +699,38 @@ def main():
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _nqb_prof():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_nqb_scan_packed_kernel.json")))
+    except Exception:
+        return None
+
+
+def _nqb_onchip():
+    d = _nqb_prof()
+    if not d:
+        return None
+    f = lambda k: float(d[k].split()[0])
+    return {"l1tex_throughput_pct_of_peak": f("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+            "l1_sector_hit_rate_pct": f("l1tex__t_sector_hit_rate.pct"),
+            "l2_throughput_pct_of_peak": f("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+            "issue_slots_pct_of_peak": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "global_ld_sectors_per_32_moves": d["derived"]["global_ld_sectors_per_32_moves"],
+            "instructions_per_32_moves": d["derived"]["instructions_per_32_moves"],
+            "source": "profiles/r1_ncu_full_nqb_scan_packed_kernel.json (n=200000 capture)"}
+
+
+def _nqb_traffic():
+    """dram bytes of one nqb_scan_packed_kernel launch in the committed capture (n=200000)"""
+    d = _nqb_prof()
+    if not d:
+        return None
+    def b(x):
+        v, u = x.split()[:2]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    return b(d["dram__bytes_read.sum"]) + b(d["dram__bytes_write.sum"])
 
 
 def _onchip():
