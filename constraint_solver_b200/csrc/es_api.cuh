@@ -26,7 +26,9 @@ struct cs_es_handle {
     EsStats* d_stats = nullptr;
     EsStats* h_stats = nullptr;
     unsigned long long* h_totals = nullptr;
-    uint16_t* h_stage = nullptr;  // pinned staging for id <-> index conversion
+    long long* d_stage64 = nullptr;  // device staging: employee ids <-> dense indices are converted on the device
+    long long* d_ids = nullptr;      // [E] sorted employee ids
+    int* d_bad = nullptr;
     size_t stage_chains = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;
@@ -69,7 +71,9 @@ void es_free(cs_es_handle* h) {
     cudaFree(h->d_stats);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->h_totals) cudaFreeHost(h->h_totals);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
+    cudaFree(h->d_stage64);
+    cudaFree(h->d_ids);
+    cudaFree(h->d_bad);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -134,31 +138,63 @@ int es_index_of(cs_es_handle* h, int64_t id) {
     return (int)(it - h->ids.begin());
 }
 
+// employee id -> dense index by binary search over the sorted id table, on the device
+__global__ void es_ids_to_index_kernel(const long long* __restrict__ rows, uint16_t* __restrict__ a, size_t total,
+                                       const long long* __restrict__ ids, int E, int* bad) {
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const long long id = rows[k];
+        int lo = 0, hi = E;
+        if (id >= 0 && id < E && ids[id] == id) lo = (int)id;  // dense ids 0..E-1: no search
+        else {
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ids[mid] < id) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo >= E || ids[lo] != id) {
+                *bad = 1;
+                lo = 0;
+            }
+        }
+        a[k] = (uint16_t)lo;
+    }
+}
+__global__ void es_index_to_ids_kernel(const uint16_t* __restrict__ a, long long* __restrict__ rows, size_t total,
+                                       const long long* __restrict__ ids) {
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+        rows[k] = ids[a[k]];
+}
+
 void es_upload(cs_es_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
     const size_t stride = h->stride;
+    CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
     for (uint32_t done = 0; done < count;) {
         const uint32_t c = (uint32_t)std::min<size_t>(count - done, h->stage_chains);
-        for (size_t k = 0; k < (size_t)c * stride; ++k) {
-            const int idx = es_index_of(h, rows[(size_t)done * stride + k]);
-            REQUIRE(idx >= 0, "solution names an employee id that is not in the employee table");
-            h->h_stage[k] = (uint16_t)idx;
-        }
-        CU(cudaMemcpyAsync(h->d_a + (size_t)(first + done) * stride, h->h_stage,
-                           (size_t)c * stride * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        const size_t total = (size_t)c * stride;
+        CU(cudaMemcpyAsync(h->d_stage64, rows + (size_t)done * stride, total * sizeof(long long),
+                           cudaMemcpyHostToDevice, h->stream));
+        es_ids_to_index_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, h->stream>>>(
+            h->d_stage64, h->d_a + (size_t)(first + done) * stride, total, h->d_ids, (int)h->ids.size(), h->d_bad);
+        CU(cudaGetLastError());
         done += c;
     }
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    REQUIRE(!bad, "solution names an employee id that is not in the employee table");
 }
 
 void es_download(cs_es_handle* h, const uint16_t* src, uint32_t first, uint32_t count, int64_t* rows) {
     const size_t stride = h->stride;
     for (uint32_t done = 0; done < count;) {
         const uint32_t c = (uint32_t)std::min<size_t>(count - done, h->stage_chains);
-        CU(cudaMemcpyAsync(h->h_stage, src + (size_t)(first + done) * stride,
-                           (size_t)c * stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+        const size_t total = (size_t)c * stride;
+        es_index_to_ids_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, h->stream>>>(
+            src + (size_t)(first + done) * stride, h->d_stage64, total, h->d_ids);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(rows + (size_t)done * stride, h->d_stage64, total * sizeof(long long),
+                           cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        for (size_t k = 0; k < (size_t)c * stride; ++k)
-            rows[(size_t)done * stride + k] = h->ids[h->h_stage[k]];
         done += c;
     }
 }
@@ -280,8 +316,11 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         CU(cudaMalloc(&h->d_stats, sizeof(EsStats)));
         CU(cudaMallocHost(&h->h_stats, sizeof(EsStats)));
         CU(cudaMallocHost(&h->h_totals, 2 * sizeof(unsigned long long)));
-        h->stage_chains = std::min<size_t>(nc, std::max<size_t>(1, (size_t)(8u << 20) / (h->stride * 2)));
-        CU(cudaMallocHost(&h->h_stage, h->stage_chains * h->stride * sizeof(uint16_t)));
+        h->stage_chains = std::min<size_t>(nc, std::max<size_t>(1, (size_t)(64u << 20) / (h->stride * 8)));
+        CU(cudaMalloc(&h->d_stage64, h->stage_chains * h->stride * sizeof(long long)));
+        CU(cudaMalloc(&h->d_ids, (size_t)E * sizeof(long long)));
+        CU(cudaMalloc(&h->d_bad, sizeof(int)));
+        CU(cudaMemcpy(h->d_ids, h->ids.data(), (size_t)E * sizeof(long long), cudaMemcpyHostToDevice));
         CU(cudaEventCreate(&h->ev0));
         CU(cudaEventCreate(&h->ev1));
         CU(cudaMemcpyAsync(h->d_hol, hol.data(), (size_t)E * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
