@@ -26,6 +26,7 @@ CS_NQ_MAX_N = 1_000_000
 CS_NQ_FLAG_GLOBAL = 1
 CS_NQ_FLAG_SCALAR = 2
 CS_NQ_FLAG_REFERENCE_PROPOSER = 4
+CS_ES_FLAG_REFERENCE_PROPOSER = 1
 CHAIN_RUNNING, CHAIN_BEST, CHAIN_STALLED, CHAIN_EMPTY = 0, 1, 2, 3
 PHILOX_INIT, PHILOX_PERTURB, PHILOX_LS, PHILOX_HOLIDAYS = 0, 1, 2, 3
 
@@ -78,7 +79,7 @@ class CsEsConfig(C.Structure):
         ("trace_capacity", C.c_uint32),
         ("seed", C.c_uint64),
         ("device", C.c_int32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -164,6 +165,7 @@ SIGNATURES = {
     "cs_es_destroy": (C.c_int32, [_VP]),
     "cs_es_last_error": (C.c_char_p, [_VP]),
     "cs_es_set_stream": (C.c_int32, [_VP, _VP]),
+    "cs_es_set_window": (C.c_int32, [_VP, C.c_uint64]),
     "cs_es_init_random": (C.c_int32, [_VP]),
     "cs_es_set_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
     "cs_es_get_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),

@@ -32,6 +32,8 @@ struct cs_es_handle {
     size_t stage_chains = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;
+    bool ref_mode = false;          // CS_ES_FLAG_REFERENCE_PROPOSER
+    unsigned long long window = 100;  // window_size, examples/employee-scheduling/src/main.rs:26
     IlsHost ils;
     std::string err;
 };
@@ -53,6 +55,10 @@ EsParams es_params(cs_es_handle* h, int first, int count) {
     p.trace_cap = (int)h->cfg.trace_capacity;
     p.work_counter = h->d_work;
     p.totals = h->d_totals;
+    p.seed = h->cfg.seed;
+    p.chain_offset = h->cfg.chain_offset;
+    p.window = h->window;
+    p.max_draws = 1ull << 16;  // bounds the reference's endless iterator (it spins forever if every candidate is tabu)
     return p;
 }
 
@@ -85,6 +91,12 @@ void es_check_range(cs_es_handle* h, uint32_t first, uint32_t count) {
             "chain range outside [0, n_chains)");
 }
 
+void es_launch_step(cs_es_handle* h, int grid, const EsParams& p) {
+    if (h->ref_mode) es_step_kernel<true><<<grid, h->threads, h->smem, h->stream>>>(p);
+    else es_step_kernel<false><<<grid, h->threads, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+}
+
 void es_rescore(cs_es_handle* h, int first, int count) {
     EsParams p = es_params(h, first, count);
     const int grid = count < h->grid_cap ? count : h->grid_cap;
@@ -110,8 +122,7 @@ void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
     CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
     const int grid = count < h->grid_cap ? count : h->grid_cap;
     CU(cudaEventRecord(h->ev0, h->stream));
-    es_step_kernel<<<grid, h->threads, h->smem, h->stream>>>(p);
-    CU(cudaGetLastError());
+    es_launch_step(h, grid, p);
     es_refresh_stats(h);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
@@ -294,11 +305,13 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin, "employee table too large for shared memory");
         const long long moves = (long long)D * E + (long long)D * (D - 1) / 2;
         h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : moves <= 32768 ? 128 : 256;
-        CU(cudaFuncSetAttribute(es_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CU(cudaFuncSetAttribute(es_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CU(cudaFuncSetAttribute(es_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        h->ref_mode = (cfg->flags & CS_ES_FLAG_REFERENCE_PROPOSER) != 0;
         CU(cudaFuncSetAttribute(es_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         CU(cudaFuncSetAttribute(es_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         int per_sm = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel, h->threads, h->smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel<false>, h->threads, h->smem));
         if (per_sm < 1) per_sm = 1;
         h->grid_cap = prop.multiProcessorCount * per_sm;
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -388,6 +401,13 @@ extern "C" int32_t cs_es_set_chains(cs_es_handle* h, uint32_t first, uint32_t co
         es_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
         h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_es_set_window(cs_es_handle* h, uint64_t window_size) {
+    return guarded(h, [&] {
+        REQUIRE(window_size >= 1, "window_size must be >= 1");
+        h->window = window_size;
     });
 }
 
@@ -555,7 +575,7 @@ extern "C" int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, i
             p.dump_h = d_dump;
             p.dump_s = d_dump + cnt;
             CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-            es_step_kernel<<<1, h->threads, h->smem, h->stream>>>(p);
+            es_launch_step(h, 1, p);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(dhard, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaMemcpyAsync(dsoft, d_dump + cnt, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
@@ -704,7 +724,7 @@ extern "C" int32_t cs_es_ils_run(cs_es_handle* h, uint32_t rounds, uint64_t ls_m
         for (uint32_t r = 0; r < rounds; ++r) {
             ils_perturb_kernel<<<ig, ILS_THREADS, h->ils.perturb_smem, h->stream>>>(ip);
             CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-            es_step_kernel<<<ls_grid, h->threads, h->smem, h->stream>>>(lp);
+            es_launch_step(h, ls_grid, lp);
             es_gather_keys_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->d_st, h->ils.d_neu_key, nullptr, nc);
             ils_accept_kernel<<<ig, ILS_THREADS, 0, h->stream>>>(ip);
             CU(cudaGetLastError());

@@ -73,6 +73,9 @@ struct EsParams {
     long long* dump_h;  // debug: every candidate's (dhard, dsoft)
     long long* dump_s;
     const unsigned int* skip;  // optional [chains]: 1 = leave the chain alone (ILS)
+    // reference mode: the reference's own random proposer + window (es_scan_ref)
+    unsigned long long seed, window, max_draws;
+    unsigned int chain_offset;
 };
 
 // per-chain shared state.  NS = min(E, D) bounds the number of PRESENT employees ("slots");
@@ -656,6 +659,128 @@ __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, 
     return key;
 }
 
+// ------------------------------------------------------------------ reference mode
+// The reference's OWN neighbourhood for scheduling: ScheduleRandomMoveProposer::iter_local_moves
+// (examples/employee-scheduling/src/lib.rs:440-491) is an endless stream of random ChangeDay
+// (weight 1) / SwapDays (weight 4) candidates drawn from a CLONE of the LocalSearch rng (:488) --
+// so every step replays the same draws from t = 0 -- filtered by the tabu set (== {current},
+// local_search.rs:155-199,319), scored, truncated to window_size (:321) and ordered by the derived
+// Ord (score, then date_to_employee by Employee.id; :29-37,323).  Candidate k uses draws
+// 3k..3k+2 of the chain's Philox stream CS_PHILOX_LS (restated in oracle/cs_oracle.c:
+// orc_es_local_search_ref).
+struct EsCand {
+    unsigned int v;  // packed (dhard, dsoft); 0xffffffff = none
+    int kind, x, y;  // change: day x -> employee index y; swap: days x < y
+};
+
+__device__ __forceinline__ unsigned int es_ref_draw(unsigned long long seed, unsigned int chain, unsigned long long t) {
+    const Philox4 b = philox_stream(seed, chain, 2u /* CS_PHILOX_LS */, t >> 2);
+    return b.v[t & 3];
+}
+
+// candidate k of the endless stream; returns false for an identity candidate (tabu)
+__device__ __forceinline__ bool es_ref_candidate(const EsSmem& s, int D, int E, unsigned long long seed,
+                                                 unsigned int chain, unsigned long long k, EsCand& c) {
+    const unsigned int u0 = es_ref_draw(seed, chain, 3 * k), u1 = es_ref_draw(seed, chain, 3 * k + 1),
+                       u2 = es_ref_draw(seed, chain, 3 * k + 2);
+    if (philox_mulhi(u0, 5u) < 1u) {  // choose_weighted over [(ChangeDay, 1), (SwapDays, 4)]
+        c.kind = 0;
+        c.x = (int)philox_mulhi(u1, (unsigned)D);
+        c.y = (int)philox_mulhi(u2, (unsigned)E);
+        return (int)s.a[c.x] != c.y;
+    }
+    c.kind = 1;
+    if (D < 2) return false;  // the reference would panic (xs[1] of a one-element sample)
+    int d1 = (int)philox_mulhi(u1, (unsigned)D), d2 = (int)philox_mulhi(u2, (unsigned)(D - 1));
+    d2 += (d2 >= d1);
+    c.x = min(d1, d2);
+    c.y = max(d1, d2);
+    return s.a[c.x] != s.a[c.y];
+}
+
+// derived Ord of ScoredSolution: score first, then the solution vector (employee indices are in
+// id order).  A candidate differs from the current rota in at most two slots.
+__device__ __forceinline__ bool es_cand_less(const EsSmem& s, const EsCand& A, const EsCand& B) {
+    if (A.v != B.v) return A.v < B.v;
+    if (A.v == 0xffffffffu) return false;
+    int pa[2], va[2], pb[2], vb[2];
+    const int na = A.kind == 0 ? 1 : 2, nb = B.kind == 0 ? 1 : 2;
+    pa[0] = A.x; va[0] = A.kind == 0 ? A.y : (int)s.a[A.y]; pa[1] = A.y; va[1] = (int)s.a[A.x];
+    pb[0] = B.x; vb[0] = B.kind == 0 ? B.y : (int)s.a[B.y]; pb[1] = B.y; vb[1] = (int)s.a[B.x];
+    int ia = 0, ib = 0;
+    while (ia < na || ib < nb) {
+        const int pA = ia < na ? pa[ia] : 1 << 30, pB = ib < nb ? pb[ib] : 1 << 30;
+        const int p = min(pA, pB);
+        const int xa = pA == p ? va[ia] : (int)s.a[p], xb = pB == p ? vb[ib] : (int)s.a[p];
+        if (xa != xb) return xa < xb;
+        ia += (pA == p);
+        ib += (pB == p);
+    }
+    return false;  // the same solution
+}
+
+// One step's window: returns the block-uniform key (v << 24 | move id) of the window's minimum,
+// ES_KEY_INF for an empty window; n_scored = candidates scored (<= window).
+__device__ long long es_scan_ref(const EsSmem& s, const EsConst& K, const u64* __restrict__ hol,
+                                 unsigned long long seed, unsigned int chain, unsigned long long window,
+                                 unsigned long long max_draws, unsigned int& n_scored) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, w = tid >> 5, nw = (nt + 31) >> 5;
+    const int D = K.D, E = K.E;
+    int* cnt = (int*)s.red;  // [nw + 1] per-warp counts of valid candidates
+    EsCand best{0xffffffffu, 0, 0, 0};
+    unsigned long long count = 0;
+    for (unsigned long long base = 0; count < window && base < max_draws; base += (unsigned)nt) {
+        EsCand c{0xffffffffu, 0, 0, 0};
+        const bool valid = es_ref_candidate(s, D, E, seed, chain, base + (unsigned)tid, c);
+        const unsigned int bal = __ballot_sync(0xffffffffu, valid);
+        int before = __popc(bal & ((1u << lane) - 1u)), total = __popc(bal);
+        if (nw > 1) {
+            __syncthreads();
+            if (lane == 0) cnt[w] = total;
+            __syncthreads();
+            total = 0;
+            for (int q = 0; q < nw; ++q) {
+                if (q < w) before += cnt[q];
+                total += cnt[q];
+            }
+        }
+        if (valid && count + (unsigned long long)before < window) {
+            if (c.kind == 0) {
+                const u64 m = s.mask[c.y];
+                c.v = m ? es_change_present_v(s, c.x, es_slot_of(s, m)) : es_change_absent_v(s, c.x, hol[c.y]);
+            } else {
+                c.v = es_swap_v(s, K, c.x, c.y);
+            }
+            if (es_cand_less(s, c, best)) best = c;
+        }
+        count += (unsigned long long)total;
+    }
+    n_scored = (unsigned int)(count < window ? count : window);
+    // block argmin under the derived Ord
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        EsCand t;
+        t.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        t.kind = __shfl_xor_sync(0xffffffffu, best.kind, o);
+        t.x = __shfl_xor_sync(0xffffffffu, best.x, o);
+        t.y = __shfl_xor_sync(0xffffffffu, best.y, o);
+        if (es_cand_less(s, t, best)) best = t;
+    }
+    if (nw > 1) {
+        EsCand* slot = (EsCand*)(s.red + 8);  // 16 B per warp, after the counts
+        __syncthreads();
+        if (lane == 0) slot[w] = best;
+        __syncthreads();
+        best = slot[0];
+        for (int q = 1; q < nw; ++q)
+            if (es_cand_less(s, slot[q], best)) best = slot[q];
+        __syncthreads();
+    }
+    if (best.v == 0xffffffffu) return ES_KEY_INF;
+    const int id = best.kind == 0 ? best.x * E + best.y : D * E + es_tri_index(D, best.x, best.y);
+    return es_key(best.v, id);
+}
+
 // per-day constants of the handle: part | cont14 | cont7 from the host table, weekday masks
 __device__ __forceinline__ void es_load_consts(const EsSmem& s, const EsConst& K, const u64* __restrict__ dayconst) {
     for (int d = threadIdx.x; d < s.dp; d += blockDim.x) {
@@ -671,6 +796,7 @@ __device__ __forceinline__ void es_load_consts(const EsSmem& s, const EsConst& K
 __device__ __forceinline__ const uint16_t* es_tri_table(const u64* dayconst) { return (const uint16_t*)(dayconst + 192); }
 
 // ------------------------------------------------------------------ the step kernel (K5)
+template <bool REF>
 __global__ void __launch_bounds__(256, 4) es_step_kernel(EsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EsConst& K = p.K;
@@ -715,10 +841,17 @@ __global__ void __launch_bounds__(256, 4) es_step_kernel(EsParams p) {
             es_prepare(s, K, p.hol);
             // non-identity candidates: every (day, employee != current) + every day pair held by
             // two different employees -- each of them is evaluated by es_scan
-            scored += (unsigned long long)(n_change - D) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
-            long long key = p.dump_h ? es_scan<true>(s, K, p.hol, tri, p.dump_h, p.dump_s)
-                                     : es_scan<false>(s, K, p.hol, tri, nullptr, nullptr);
-            key = es_block_min(key, s.red);
+            long long key;
+            if (REF && !p.dump_h) {  // the reference's sampled window instead of the whole neighbourhood
+                unsigned int nsc = 0;
+                key = es_scan_ref(s, K, p.hol, p.seed, p.chain_offset + (unsigned)chain, p.window, p.max_draws, nsc);
+                scored += nsc;
+            } else {
+                scored += (unsigned long long)(n_change - D) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
+                key = p.dump_h ? es_scan<true>(s, K, p.hol, tri, p.dump_h, p.dump_s)
+                               : es_scan<false>(s, K, p.hol, tri, nullptr, nullptr);
+                key = es_block_min(key, s.red);
+            }
             if (p.dump_h) break;
             if (key == ES_KEY_INF) {  // empty neighbourhood, local_search.rs:336-338
                 status = 3;

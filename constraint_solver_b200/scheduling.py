@@ -61,7 +61,7 @@ class ScheduleChains:
 
     def __init__(self, n_days: int, employees: Sequence[int], *, start_weekday: int = 0,
                  holidays=(), n_chains: int = 1, seed: int = 42, chain_offset: int = 0,
-                 trace_capacity: int = 0, device: int = -1):
+                 trace_capacity: int = 0, device: int = -1, reference_proposer: bool = False):
         self._lib = L.load()
         self.n_days = int(n_days)
         self.n_slots = self.n_days + 1
@@ -75,7 +75,8 @@ class ScheduleChains:
         hd = np.ascontiguousarray(hol[:, 1]) if len(hol) else np.zeros(1, np.int64)
         cfg = L.CsEsConfig(n_days=n_days, n_employees=self.n_employees, start_weekday=start_weekday,
                            n_chains=n_chains, chain_offset=chain_offset,
-                           trace_capacity=trace_capacity, seed=seed, device=device, reserved=0)
+                           trace_capacity=trace_capacity, seed=seed, device=device,
+                           flags=L.CS_ES_FLAG_REFERENCE_PROPOSER if reference_proposer else 0)
         ids = np.ascontiguousarray(np.asarray(list(employees), dtype=np.int64))
         h = C.c_void_p()
         rc = self._lib.cs_es_create(C.byref(cfg), _ptr(ids), _ptr(he), _ptr(hd), len(hol), C.byref(h))
@@ -106,6 +107,10 @@ class ScheduleChains:
 
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.cs_es_set_stream(self._h, C.c_void_p(cuda_stream)), "cs_es_set_stream")
+
+    def set_window(self, window_size: int):
+        """window_size of LocalSearch::new; only the reference proposer truncates (main.rs:26: 100)"""
+        self._check(self._lib.cs_es_set_window(self._h, window_size), "cs_es_set_window")
 
     def init_random(self):
         self._check(self._lib.cs_es_init_random(self._h), "cs_es_init_random")

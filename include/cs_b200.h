@@ -38,7 +38,7 @@ extern "C" {
 #define CS_ERR_STATE (-5)
 #define CS_ERR_UNSUPPORTED (-6)
 
-#define CS_ABI_VERSION 2
+#define CS_ABI_VERSION 3
 
 /* Largest board the shared-memory-resident chain kernels take (one CTA holds rows,
  * per-column line sums and both diagonal counter arrays in <= 227 KB). */
@@ -253,6 +253,14 @@ typedef struct cs_es_handle cs_es_handle;
 #define CS_ES_MAX_DAYS 64u
 #define CS_ES_CHANGE 0u /* ChangeDay: a = day, b = index into the sorted employee table, lib.rs:466-470 */
 #define CS_ES_SWAP 1u   /* SwapDays: a < b days, lib.rs:471-478 */
+/* Reference mode: the reference's own move proposer -- ScheduleRandomMoveProposer, the one get_ils
+ * installs (examples/employee-scheduling/src/lib.rs:60, :440-491): an endless stream of random
+ * ChangeDay (weight 1) / SwapDays (weight 4) candidates drawn from a CLONE of the LocalSearch rng
+ * (:488; every step replays the same draws) -- tabu-filtered, truncated to window_size candidates
+ * (local_search.rs:321) and ordered by the derived Ord (score, then date_to_employee), :323.
+ * Random choices come from the chain's Philox stream CS_PHILOX_LS.  Without the flag the device
+ * scans the FULL change + swap neighbourhood (ScheduleMoveProposer's precedent, lib.rs:493-559). */
+#define CS_ES_FLAG_REFERENCE_PROPOSER 1u
 
 typedef struct cs_es_config {
     uint32_t n_days;         /* D = end_date - start_date + 1, 1..CS_ES_MAX_DAYS */
@@ -263,7 +271,7 @@ typedef struct cs_es_config {
     uint32_t trace_capacity;
     uint64_t seed;
     int32_t device;
-    uint32_t reserved;
+    uint32_t flags;          /* CS_ES_FLAG_* */
 } cs_es_config;
 
 typedef struct cs_es_move {
@@ -316,6 +324,9 @@ int32_t cs_es_enumerate(cs_es_handle* h, uint32_t chain, cs_es_move* moves, uint
  * n_days*n_employees change entries then n_days*(n_days-1)/2 swap entries */
 int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, int64_t* dhard, int64_t* dsoft,
                                    uint64_t cap, uint64_t* n_out);
+/* window_size of LocalSearch::new (local_search.rs:281); only reference mode truncates the
+ * neighbourhood (default 100, examples/employee-scheduling/src/main.rs:26). */
+int32_t cs_es_set_window(cs_es_handle* h, uint64_t window_size);
 /* hot path: enumerate change + swap moves, delta-score the 8 constraints, lexicographic
  * (hard, soft, move id) argmin, accept (local_search.rs:315-335) */
 int32_t cs_es_step(cs_es_handle* h, uint32_t n_steps, cs_es_step_stats* stats);

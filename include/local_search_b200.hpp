@@ -510,12 +510,13 @@ inline void check(cs_es_handle* h, int32_t rc, const char* where) {
 }
 
 inline Handle make_handle(NaiveDate start, NaiveDate end, const std::vector<Employee>& employees,
-                          const EmployeeToHolidays& holidays, uint32_t n_chains, uint64_t seed, uint32_t chain_offset = 0) {
+                          const EmployeeToHolidays& holidays, uint32_t n_chains, uint64_t seed, uint32_t chain_offset = 0,
+                          uint32_t flags = 0) {
     cs_es_config cfg{};
     cfg.n_days = (uint32_t)(end.days - start.days + 1);
     cfg.n_employees = (uint32_t)employees.size();
     cfg.start_weekday = start.num_days_from_monday();
-    cfg.n_chains = n_chains; cfg.chain_offset = chain_offset; cfg.seed = seed; cfg.device = -1;
+    cfg.n_chains = n_chains; cfg.chain_offset = chain_offset; cfg.seed = seed; cfg.device = -1; cfg.flags = flags;
     std::vector<int64_t> ids, he, hd;
     for (const Employee& e : employees) ids.push_back(e.id);
     for (auto& kv : holidays)
@@ -570,11 +571,11 @@ public:
     }
 };
 
-// The device always scans the FULL change + swap neighbourhood (ScheduleMoveProposer's
-// precedent, lib.rs:493-559); ScheduleRandomMoveProposer (lib.rs:429-491) is accepted for
-// signature compatibility and means the same thing here.
-struct ScheduleRandomMoveProposer {};
-struct ScheduleMoveProposer { std::vector<Employee> employees; };
+// ScheduleRandomMoveProposer (lib.rs:429-491, the one get_ils installs, :60) = the reference's
+// sampled window on the device (CS_ES_FLAG_REFERENCE_PROPOSER); ScheduleMoveProposer
+// (lib.rs:493-559, exhaustive) = the FULL change + swap neighbourhood, the north-star hot path.
+struct ScheduleRandomMoveProposer { static constexpr uint32_t flags = CS_ES_FLAG_REFERENCE_PROPOSER; };
+struct ScheduleMoveProposer { std::vector<Employee> employees; static constexpr uint32_t flags = 0; };
 struct SchedulePerturbation {};
 
 }  // namespace employee_scheduling
@@ -595,14 +596,18 @@ class ScheduleLocalSearch {
 public:
     // LocalSearch::new(...) + what get_ils knows about the rota (lib.rs:57-81): the device needs
     // the calendar and the employee table up front.
-    ScheduleLocalSearch(employee_scheduling::ScheduleRandomMoveProposer, const employee_scheduling::ScheduleSolutionScoreCalculator& ssc,
-                        uint64_t max_iterations, size_t /*window_size*/, size_t /*best_solutions_capacity*/,
+    template <class MoveProposerT>
+    ScheduleLocalSearch(const MoveProposerT&, const employee_scheduling::ScheduleSolutionScoreCalculator& ssc,
+                        uint64_t max_iterations, size_t window_size, size_t /*best_solutions_capacity*/,
                         size_t /*all_solutions_capacity*/, uint64_t /*all_solution_iteration_expiry*/, PhiloxRng rng,
                         employee_scheduling::NaiveDate start_date, employee_scheduling::NaiveDate end_date,
                         std::vector<employee_scheduling::Employee> employees, uint32_t n_chains = 1)
         : start_(start_date), end_(end_date), employees_(std::move(employees)), max_iterations_(max_iterations) {
         std::sort(employees_.begin(), employees_.end());
-        h_ = employee_scheduling::make_handle(start_, end_, employees_, ssc.holidays(), n_chains, rng.seed, rng.chain);
+        h_ = employee_scheduling::make_handle(start_, end_, employees_, ssc.holidays(), n_chains, rng.seed, rng.chain,
+                                              MoveProposerT::flags);
+        if (MoveProposerT::flags & CS_ES_FLAG_REFERENCE_PROPOSER)
+            employee_scheduling::check(h_.get(), cs_es_set_window(h_.get(), window_size), "cs_es_set_window");
     }
     employee_scheduling::Scored execute(const employee_scheduling::ScheduleSolution& start, uint64_t allow_no_improvement_for) {
         std::vector<int64_t> in = employee_scheduling::ids_of(start.date_to_employee), best(slots());

@@ -27,7 +27,7 @@ pub struct cs_nq_config {
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct cs_es_config {
     pub n_days: u32, pub n_employees: u32, pub start_weekday: u32, pub n_chains: u32,
-    pub chain_offset: u32, pub trace_capacity: u32, pub seed: u64, pub device: i32, pub reserved: u32,
+    pub chain_offset: u32, pub trace_capacity: u32, pub seed: u64, pub device: i32, pub flags: u32,
 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -81,6 +81,7 @@ extern "C" {
     pub fn cs_es_set_chains(h: *mut cs_es_handle, first: u32, count: u32, rows: *const i64) -> i32;
     pub fn cs_es_score_full(h: *mut cs_es_handle, chain: u32, hard: *mut i64, soft: *mut i64,
                             terms: *mut i64) -> i32;
+    pub fn cs_es_set_window(h: *mut cs_es_handle, window_size: u64) -> i32;
     pub fn cs_es_local_search_one(h: *mut cs_es_handle, start: *const i64, allow: u64,
                                   max_iterations: u64, best: *mut i64, best_hard: *mut i64,
                                   best_soft: *mut i64) -> i32;

@@ -109,7 +109,7 @@ impl B200ScheduleLocalSearch {
                max_iterations: u64, seed: u64) -> Self {
         let cfg = ffi::cs_es_config {
             n_days, n_employees: employees.len() as u32, start_weekday, n_chains: 1, chain_offset: 0,
-            trace_capacity: 0, seed, device: -1, reserved: 0,
+            trace_capacity: 0, seed, device: -1, flags: 1 /* CS_ES_FLAG_REFERENCE_PROPOSER: get_ils installs ScheduleRandomMoveProposer */,
         };
         let he: Vec<i64> = holidays.iter().map(|h| h.0).collect();
         let hd: Vec<i64> = holidays.iter().map(|h| h.1).collect();

@@ -497,6 +497,129 @@ int64_t orc_es_local_search(int64_t* a, int64_t D, int start_weekday, const int6
     return steps;
 }
 
+/* LocalSearch::execute (local-search/src/local_search.rs:301-342) with the reference's OWN
+ * scheduling proposer, ScheduleRandomMoveProposer::iter_local_moves
+ * (examples/employee-scheduling/src/lib.rs:440-491): an endless stream of random ChangeDay
+ * (weight 1) / SwapDays (weight 4) candidates (:435, :459-478) drawn from a CLONE of the
+ * LocalSearch rng (:488) -- the solver rng never advances, so EVERY step replays the same draws
+ * from t = 0 -- each a full clone of the rota, filtered by the tabu set (== {current},
+ * local_search.rs:155-199,319), full re-scored (:320), truncated to window_size (:321) and
+ * sorted by the derived Ord (score, then date_to_employee by Employee.id; :29-37,323).
+ * Draw restatement (rand 0.8.5 is un-vendored: parity unpinned at the RNG boundary): candidate k
+ * uses draws 3k..3k+2 of Philox stream (seed, chain, purpose 2):
+ *   choose_weighted     -> mulhi(u,5) < 1 ? ChangeDay : SwapDays
+ *   ChangeDay           -> day = mulhi(u,D) (scored days only, :466), employee = employees[mulhi(u,E)]
+ *   SwapDays            -> choose_multiple(2): d1 = mulhi(u,D), d2 = mulhi(u,D-1), d2 += (d2 >= d1)
+ * max_draws bounds the endless iterator: the reference spins forever when every candidate is tabu
+ * (one employee); D = 1 SwapDays candidates are skipped (the reference indexes xs[1] and panics).
+ * a: in = start, out = best_solution.  trace: kind, x, y (change: day, employee INDEX; swap:
+ * min day, max day) and the score after each accepted step.  Returns the accepted steps;
+ * *scored_out (optional) = candidates scored in total. */
+int64_t orc_es_local_search_ref(int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                                const int64_t* hol_day, int64_t n_hol, const int64_t* employees,
+                                int64_t E, uint64_t seed, uint32_t chain,
+                                uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                                uint64_t window_size, uint64_t max_draws, int64_t* best_hard,
+                                int64_t* best_soft, int64_t* current_out, int64_t* trace_kind,
+                                int64_t* trace_x, int64_t* trace_y, int64_t* trace_hard,
+                                int64_t* trace_soft, int64_t cap, int64_t* scored_out) {
+    const size_t bytes = sizeof(int64_t) * (size_t)(D > 0 ? D : 1);
+    int64_t* current = (int64_t*)malloc(bytes);
+    int64_t* best = (int64_t*)malloc(bytes);
+    int64_t* cand = (int64_t*)malloc(bytes);
+    int64_t* nb = (int64_t*)malloc(bytes);
+    memcpy(current, a, bytes);
+    int64_t ch, cs;
+    orc_es_score(current, D, start_weekday, hol_emp, hol_day, n_hol, &ch, &cs);
+    memcpy(best, current, bytes);
+    int64_t bh = ch, bs = cs, steps = 0, scored = 0;
+    uint64_t no_improvement_for = 0;
+    for (uint64_t it = 0; it < max_iterations; ++it) {
+        if (ch == 0 && cs == 0) { /* local_search.rs:311-314 */
+            memcpy(best, current, bytes);
+            bh = ch;
+            bs = cs;
+            break;
+        }
+        int have = 0;
+        int64_t nh = 0, ns = 0, nk = 0, nx = 0, ny = 0;
+        uint64_t taken = 0;
+        for (uint64_t k = 0; k < max_draws && taken < window_size; ++k) { /* rng.clone(): t restarts at 0 */
+            const uint32_t u0 = orc_philox_draw(seed, chain, 2u, 3 * k);
+            const uint32_t u1 = orc_philox_draw(seed, chain, 2u, 3 * k + 1);
+            const uint32_t u2 = orc_philox_draw(seed, chain, 2u, 3 * k + 2);
+            int64_t kind, x, y;
+            memcpy(cand, current, bytes); /* self.solution.clone(), lib.rs:464 */
+            if ((((uint64_t)u0 * 5u) >> 32) < 1) {
+                kind = ORC_ES_CHANGE;
+                x = (int64_t)(((uint64_t)u1 * (uint64_t)D) >> 32);
+                y = (int64_t)(((uint64_t)u2 * (uint64_t)E) >> 32);
+                cand[x] = employees[y];
+            } else {
+                kind = ORC_ES_SWAP;
+                if (D < 2) continue;
+                int64_t d1 = (int64_t)(((uint64_t)u1 * (uint64_t)D) >> 32);
+                int64_t d2 = (int64_t)(((uint64_t)u2 * (uint64_t)(D - 1)) >> 32);
+                d2 += (d2 >= d1);
+                x = d1 < d2 ? d1 : d2;
+                y = d1 < d2 ? d2 : d1;
+                const int64_t t = cand[x];
+                cand[x] = cand[y];
+                cand[y] = t;
+            }
+            if (memcmp(cand, current, bytes) == 0) continue; /* tabu == {current}, local_search.rs:319 */
+            ++taken;
+            ++scored;
+            int64_t h, s_;
+            orc_es_score(cand, D, start_weekday, hol_emp, hol_day, n_hol, &h, &s_);
+            int better = !have || h < nh || (h == nh && s_ < ns);
+            if (have && h == nh && s_ == ns) { /* derived Ord: lexicographic date_to_employee */
+                for (int64_t q = 0; q < D; ++q)
+                    if (cand[q] != nb[q]) {
+                        better = cand[q] < nb[q];
+                        break;
+                    }
+            }
+            if (better) {
+                have = 1;
+                nh = h; ns = s_; nk = kind; nx = x; ny = y;
+                memcpy(nb, cand, bytes);
+            }
+        }
+        if (!have) break; /* empty window, local_search.rs:336-338 */
+        if (nh < ch || (nh == ch && ns < cs)) {
+            memcpy(best, nb, bytes);
+            bh = nh;
+            bs = ns;
+            no_improvement_for = 0;
+        } else {
+            no_improvement_for += 1;
+            if (no_improvement_for >= allow_no_improvement_for) break;
+        }
+        memcpy(current, nb, bytes);
+        ch = nh;
+        cs = ns;
+        if (steps < cap) {
+            if (trace_kind) trace_kind[steps] = nk;
+            if (trace_x) trace_x[steps] = nx;
+            if (trace_y) trace_y[steps] = ny;
+            if (trace_hard) trace_hard[steps] = nh;
+            if (trace_soft) trace_soft[steps] = ns;
+        }
+        ++steps;
+    }
+    memcpy(a, best, bytes);
+    if (best_hard) *best_hard = bh;
+    if (best_soft) *best_soft = bs;
+    if (current_out) memcpy(current_out, current, bytes);
+    if (scored_out) *scored_out = scored;
+    free(current);
+    free(best);
+    free(cand);
+    free(nb);
+    return steps;
+}
+
 int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
                                const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
                                const int64_t* employees, int64_t E, int kind, const int64_t* x,
@@ -842,6 +965,8 @@ typedef struct {
     const int64_t *he, *hd, *emp;
     int64_t nh;
     uint64_t allow, iters;
+    uint64_t ref_window, ref_max_draws, seed; /* ref_window > 0: the reference's own proposer */
+    uint32_t chain;
 } es_ils_ctx;
 
 /* the ILS vectors of the scheduling problem hold employee INDICES (0..E-1) over D+1 slots */
@@ -850,8 +975,13 @@ static int64_t es_ils_ls(void* c, int64_t* sol) {
     int64_t* a = (int64_t*)malloc(sizeof(int64_t) * (size_t)x->D);
     for (int64_t i = 0; i < x->D; ++i) a[i] = x->emp[sol[i]];
     int64_t bh = 0, bs = 0;
-    orc_es_local_search(a, x->D, x->wd, x->he, x->hd, x->nh, x->emp, x->E, x->allow, x->iters, &bh,
-                        &bs, NULL, NULL, NULL, NULL, NULL, NULL, 0);
+    if (x->ref_window)
+        orc_es_local_search_ref(a, x->D, x->wd, x->he, x->hd, x->nh, x->emp, x->E, x->seed, x->chain, x->allow,
+                                x->iters, x->ref_window, x->ref_max_draws, &bh, &bs, NULL, NULL, NULL, NULL,
+                                NULL, NULL, 0, NULL);
+    else
+        orc_es_local_search(a, x->D, x->wd, x->he, x->hd, x->nh, x->emp, x->E, x->allow, x->iters, &bh,
+                            &bs, NULL, NULL, NULL, NULL, NULL, NULL, 0);
     for (int64_t i = 0; i < x->D; ++i) {
         int64_t e = 0;
         while (x->emp[e] != a[i]) ++e;
@@ -872,8 +1002,21 @@ int64_t orc_es_ils(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
                    uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
                    int64_t* best_idx /*[D+1] employee indices*/, int64_t* best_hard,
                    int64_t* best_soft, int64_t* round_new_key, int64_t* round_choice) {
+    return orc_es_ils_ref(seed, chain, D, start_weekday, hol_emp, hol_day, n_hol, employees, E, ls_max_iterations,
+                          allow_no_improvement_for, rounds, best_cap, best_idx, best_hard, best_soft, round_new_key,
+                          round_choice, 0, 0);
+}
+
+/* orc_es_ils with LocalSearch::execute running the reference's own proposer when ref_window > 0 */
+int64_t orc_es_ils_ref(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
+                       const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                       const int64_t* employees, int64_t E, uint64_t ls_max_iterations,
+                       uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
+                       int64_t* best_idx, int64_t* best_hard, int64_t* best_soft,
+                       int64_t* round_new_key, int64_t* round_choice, uint64_t ref_window,
+                       uint64_t ref_max_draws) {
     es_ils_ctx ctx = {D, E, start_weekday, hol_emp, hol_day, employees, n_hol,
-                      allow_no_improvement_for, ls_max_iterations};
+                      allow_no_improvement_for, ls_max_iterations, ref_window, ref_max_draws, seed, chain};
     int64_t* current = (int64_t*)malloc(sizeof(int64_t) * (size_t)(D + 1));
     for (int64_t s = 0; s <= D; ++s) /* same draws as orc_es_init, as indices */
         current[s] = (int64_t)(((uint64_t)orc_philox_draw(seed, chain, 0u, (uint64_t)s) * (uint64_t)E) >> 32);

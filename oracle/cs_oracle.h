@@ -147,6 +147,26 @@ int64_t orc_es_ils(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
                    int64_t* best_idx, int64_t* best_hard, int64_t* best_soft,
                    int64_t* round_new_key, int64_t* round_choice);
 
+/* LocalSearch::execute with the reference's OWN scheduling proposer
+ * (ScheduleRandomMoveProposer, examples/employee-scheduling/src/lib.rs:440-491: endless random
+ * ChangeDay / SwapDays stream from a CLONED rng), window (.take(window_size)) and derived-Ord
+ * tie-break; see cs_oracle.c. */
+int64_t orc_es_local_search_ref(int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                                const int64_t* hol_day, int64_t n_hol, const int64_t* employees,
+                                int64_t E, uint64_t seed, uint32_t chain,
+                                uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                                uint64_t window_size, uint64_t max_draws, int64_t* best_hard,
+                                int64_t* best_soft, int64_t* current_out, int64_t* trace_kind,
+                                int64_t* trace_x, int64_t* trace_y, int64_t* trace_hard,
+                                int64_t* trace_soft, int64_t cap, int64_t* scored_out);
+int64_t orc_es_ils_ref(uint64_t seed, uint32_t chain, int64_t D, int start_weekday,
+                       const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                       const int64_t* employees, int64_t E, uint64_t ls_max_iterations,
+                       uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,
+                       int64_t* best_idx, int64_t* best_hard, int64_t* best_soft,
+                       int64_t* round_new_key, int64_t* round_choice, uint64_t ref_window,
+                       uint64_t ref_max_draws);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ def lib():
         _lib.orc_nq_ils.restype = I64
         _lib.orc_nq_local_search_ref.restype = I64
         _lib.orc_es_ils.restype = I64
+        _lib.orc_es_local_search_ref.restype = I64
+        _lib.orc_es_ils_ref.restype = I64
     return _lib
 
 
@@ -284,6 +286,46 @@ def es_ils(seed, chain, D, employees, start_weekday=0, holidays=None, ls_max_ite
                          I64(len(he)), _p(employees), I64(len(employees)), U64(ls_max_iterations),
                          U64(allow_no_improvement_for), U64(rounds), C.c_int(best_cap), _p(best),
                          C.byref(bh), C.byref(bs), _p(rn), _p(rc))
+    r = int(r)
+    return dict(rounds=r, best=employees[best], best_hard=int(bh.value), best_soft=int(bs.value),
+                round_new_key=rn[:r], round_choice=rc[:r])
+
+
+def es_local_search_ref(a, employees, seed, chain, start_weekday=0, holidays=None,
+                        allow_no_improvement_for=20, max_iterations=1000, window_size=100,
+                        max_draws=1 << 16, trace_cap=0):
+    """LocalSearch::execute with the reference's own scheduling proposer (random ChangeDay /
+    SwapDays stream from a cloned rng), window and derived-Ord tie-break."""
+    a = _i64(a).copy()
+    employees = _i64(employees)
+    he, hd = _hol(holidays)
+    D = len(a)
+    cur = np.zeros(max(D, 1), dtype=np.int64)
+    bh, bs, sc = I64(0), I64(0), I64(0)
+    tr = [np.zeros(max(trace_cap, 1), dtype=np.int64) for _ in range(5)]
+    steps = lib().orc_es_local_search_ref(
+        _p(a), I64(D), C.c_int(start_weekday), _p(he), _p(hd), I64(len(he)), _p(employees),
+        I64(len(employees)), U64(seed), C.c_uint32(chain), U64(allow_no_improvement_for),
+        U64(max_iterations), U64(window_size), U64(max_draws), C.byref(bh), C.byref(bs), _p(cur),
+        _p(tr[0]), _p(tr[1]), _p(tr[2]), _p(tr[3]), _p(tr[4]), I64(trace_cap), C.byref(sc))
+    k = min(int(steps), trace_cap)
+    return dict(best=a, best_hard=int(bh.value), best_soft=int(bs.value), current=cur[:D],
+                steps=int(steps), scored=int(sc.value), trace_kind=tr[0][:k], trace_x=tr[1][:k],
+                trace_y=tr[2][:k], trace_hard=tr[3][:k], trace_soft=tr[4][:k])
+
+
+def es_ils_ref(seed, chain, D, employees, start_weekday=0, holidays=None, ls_max_iterations=1000,
+               allow_no_improvement_for=20, rounds=50, best_cap=64, window_size=100, max_draws=1 << 16):
+    employees = _i64(employees)
+    he, hd = _hol(holidays)
+    best = np.zeros(D + 1, dtype=np.int64)
+    rn = np.zeros(max(rounds, 1), dtype=np.int64)
+    rc = np.zeros(max(rounds, 1), dtype=np.int64)
+    bh, bs = I64(0), I64(0)
+    r = lib().orc_es_ils_ref(U64(seed), C.c_uint32(chain), I64(D), C.c_int(start_weekday), _p(he), _p(hd),
+                             I64(len(he)), _p(employees), I64(len(employees)), U64(ls_max_iterations),
+                             U64(allow_no_improvement_for), U64(rounds), C.c_int(best_cap), _p(best),
+                             C.byref(bh), C.byref(bs), _p(rn), _p(rc), U64(window_size), U64(max_draws))
     r = int(r)
     return dict(rounds=r, best=employees[best], best_hard=int(bh.value), best_soft=int(bs.value),
                 round_new_key=rn[:r], round_choice=rc[:r])

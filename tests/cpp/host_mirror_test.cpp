@@ -216,7 +216,9 @@ static void gpu_tests() {
         es::EmployeeToHolidays hol;
         hol[{2}] = {start + 4, start + 11};
         es::ScheduleSolutionScoreCalculator calc(hol);
-        ScheduleLocalSearch ls({}, calc, 1000, 100, 64, 100000, 1000, PhiloxRng::seed_from_u64(5), start, end, emp);
+        // ScheduleMoveProposer = the exhaustive neighbourhood (lib.rs:493-559)
+        ScheduleLocalSearch ls(es::ScheduleMoveProposer{emp}, calc, 1000, 100, 64, 100000, 1000, PhiloxRng::seed_from_u64(5), start,
+                               end, emp);
         const es::ScheduleSolution s0 = rota([](int i) { return (int64_t)((i * 5 + i / 3) % 7); });
         const es::Scored got = ls.execute(s0, 20);
         std::vector<int64_t> a = es::ids_of(s0.date_to_employee), ids = es::ids_of(emp);
@@ -228,6 +230,23 @@ static void gpu_tests() {
         ASSERT_EQ(got.score.soft_score, (double)bs);
         ASSERT_EQ(es::ids_of(got.solution.date_to_employee), a);
 
+        // ScheduleRandomMoveProposer = the reference's own sampled window (lib.rs:440-491), against
+        // the oracle's literal restatement over the same Philox stream
+        {
+            ScheduleLocalSearch rls(es::ScheduleRandomMoveProposer{}, calc, 200, 100, 64, 100000, 1000, PhiloxRng::seed_from_u64(5),
+                                    start, end, emp);
+            const es::Scored rgot = rls.execute(s0, 20);
+            std::vector<int64_t> ra = es::ids_of(s0.date_to_employee);
+            int64_t rh = 0, rs = 0;
+            orc_es_local_search_ref(ra.data(), 31, 0, he, hd, 2, ids.data(), 7, 5, 0, 20, 200, 100, 1u << 16, &rh, &rs, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+            ASSERT_EQ(rgot.score.hard_score, (double)rh);
+            ASSERT_EQ(rgot.score.soft_score, (double)rs);
+            std::vector<int64_t> got_ids = es::ids_of(rgot.solution.date_to_employee);
+            got_ids.resize(31);
+            ra.resize(31);
+            ASSERT_EQ(got_ids, ra);
+        }
         es::MainArgs args;
         args.start_date = start;
         args.end_date = end;

@@ -141,3 +141,43 @@ def test_es_local_search_trace_replays():
             cur[x], cur[y] = cur[y], cur[x]
         assert orc.es_score(cur, 0, hol) == (h, s)
     assert np.array_equal(cur, res["current"])
+
+
+def test_scheduling_reference_proposer_restatement_against_a_python_rewrite():
+    """orc_es_local_search_ref (random ChangeDay / SwapDays stream from a cloned rng, window,
+    derived-Ord tie-break; examples/employee-scheduling/src/lib.rs:440-491,
+    local_search.rs:315-335) against an independent pure-Python rewrite of the same step."""
+    D, ids, wd, hol, window, seed, chain = 12, np.array([2, 5, 9], dtype=np.int64), 3, [(5, 4)], 25, 77, 4
+    start = ids[np.random.default_rng(0).integers(0, 3, size=D)]
+    ref = orc.es_local_search_ref(start, ids, seed, chain, wd, hol, allow_no_improvement_for=4,
+                                  max_iterations=6, window_size=window, trace_cap=8)
+    cur = start.copy()
+    score = orc.es_score(cur, wd, hol)
+    steps, no_improve = 0, 0
+    for _ in range(6):
+        if score == (0, 0):
+            break
+        cands, k = [], 0
+        while len(cands) < window and k < 1 << 16:
+            u = [orc.philox_stream(seed, chain, 2, (3 * k + j) // 4)[(3 * k + j) % 4] for j in range(3)]
+            k += 1
+            c = cur.copy()
+            if (u[0] * 5) >> 32 < 1:
+                c[(u[1] * D) >> 32] = ids[(u[2] * len(ids)) >> 32]
+            else:
+                d1, d2 = (u[1] * D) >> 32, (u[2] * (D - 1)) >> 32
+                d2 += d2 >= d1
+                c[d1], c[d2] = c[d2], c[d1]
+            if not np.array_equal(c, cur):
+                cands.append((orc.es_score(c, wd, hol), c.tolist()))
+        nb_score, nb = min(cands)                                  # (score, solution) derived Ord
+        if nb_score < score:
+            no_improve = 0
+        else:
+            no_improve += 1
+            if no_improve >= 4:
+                break
+        cur, score = np.array(nb, dtype=np.int64), nb_score
+        assert (int(ref["trace_hard"][steps]), int(ref["trace_soft"][steps])) == score
+        steps += 1
+    assert steps == ref["steps"] and np.array_equal(cur, ref["current"])
