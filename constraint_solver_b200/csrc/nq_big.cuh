@@ -269,6 +269,14 @@ __global__ void nqb_pack_kernel(NqBig b) {
 constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = 8 * NQBP_TI;  // 8 warps x TI slots
 constexpr int NQBP_INF16 = 0x3fff, NQBP_BIAS = 128;
 
+// the lane-consecutive operand is read once per tile: keep it out of L1 so the gather windows
+// (shared by the CTA's warps) stay resident
+__device__ __forceinline__ unsigned int nqbp_ld_stream(const unsigned char* p) {
+    unsigned int v;
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 template <bool DUMP>
 __global__ void __launch_bounds__(256, 2) nqb_scan_packed_kernel(NqBig b) {
     if (*b.maxcount > (unsigned)NQBP_MAX_COUNT) return;  // a line too long for byte sums: nqb_scan_kernel runs
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(256, 2) nqb_scan_packed_kernel(NqBig b) {
             unsigned T[TI];
 #pragma unroll
             for (int a = 0; a < TI; ++a)
-                T[a] = __ldcs((const unsigned*)(Q + pv1[a] + dj)) + __ldcs((const unsigned*)(Q + pv2[a] + dj));
+                T[a] = nqbp_ld_stream(Q + pv1[a] + dj) + nqbp_ld_stream(Q + pv2[a] + dj);
             unsigned TP[NQBP_TJ][TI / 4];  // byte transpose: TP[b][g] = slots 4g..4g+3 at j_b
 #pragma unroll
             for (int g4 = 0; g4 < TI / 4; ++g4) {
