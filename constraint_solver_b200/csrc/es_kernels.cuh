@@ -113,12 +113,13 @@ struct EsSmem {
     signed char* s3t;      // [DP][ES_TCOLS] S3 delta ... to a present employee whose total has rank j
     signed char* s4t;      // [DP][ES_WCOLS] S4 delta ... to a present employee whose weekend count has rank j
     signed char* s4s;      // [DP][ES_WCOLS] S4 delta of SWAPPING weekend day d with a weekday of such an employee
+    uint16_t* ga;          // [DP][NS] pass A's gains of giving day d to slot: gh | gs << 5 | (s2 + 16) << 8 (swaps reuse them)
     int ns, dp;
 };
 
 struct EsLayout {
     size_t mask, a, hist, occ, occT, fmask, misc, red, day, eq, smask, shol, semp, srk, val, dwd, dslot, dayb, base,
-        baseW, s2t, s3t, s4t, s4s, total;
+        baseW, s2t, s3t, s4t, s4s, ga, total;
     int ns, dp;
 };
 __host__ __device__ inline size_t es_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -154,6 +155,8 @@ __host__ __device__ inline EsLayout es_layout(int D, int E) {
     L.s3t = o;     o += dp * ES_TCOLS;
     L.s4t = o;     o += dp * ES_WCOLS;
     L.s4s = o;     o += dp * ES_WCOLS;
+    o = es_align(o, 8);
+    L.ga = o;      o += dp * (size_t)L.ns * 2;
     L.total = es_align(o, 16);
     return L;
 }
@@ -195,6 +198,7 @@ __device__ __forceinline__ EsSmem es_carve(unsigned char* p, int D, int E) {
     s.s3t = (signed char*)(p + L.s3t);
     s.s4t = (signed char*)(p + L.s4t);
     s.s4s = (signed char*)(p + L.s4s);
+    s.ga = (uint16_t*)(p + L.ga);
     return s;
 }
 
@@ -482,16 +486,23 @@ __device__ __forceinline__ unsigned int es_w_to_v(unsigned int w) {
     return ((unsigned)(0x8000 - 64 + (int)(w >> 15)) << 16) | (unsigned)(0x8000 - 256 + (int)((w >> 6) & 0x1ffu));
 }
 
-// change: day d goes to the PRESENT employee of `slot` (not the day's current one)
-__device__ __forceinline__ unsigned int es_change_present_v(const EsSmem& s, int d, int slot) {
+// change: day d goes to the PRESENT employee of `slot` (not the day's current one).  ga = the
+// receiver-side parts (hard gain, S1 gain, S2 delta) packed for the swap pass.
+__device__ __forceinline__ unsigned int es_change_present_v(const EsSmem& s, int d, int slot, unsigned int& ga) {
     const u64 m = s.smask[slot];
     const u64* q = s.eq + slot * 4;
     const int gh = (int)((s.shol[slot] >> d) & 1ull) + __popcll(m & s.part[d]) + __popcll(q[0] & s.cont14[d]);
     const int gs = __popcll(q[2] & s.cont7[d]);
     const int cn = __popcll(m & s.wdm[d]);
+    const int s2 = (int)s.s2t[d * ES_CBINS + cn];
+    ga = (unsigned)gh | ((unsigned)gs << 5) | ((unsigned)(s2 + 16) << 8);
     return s.base[d] + ((unsigned)gh << 16) +
-           (unsigned)(gs + (int)s.s2t[d * ES_CBINS + cn] + (int)s.s3t[d * ES_TCOLS + (int)s.srk[2 * slot]] +
+           (unsigned)(gs + s2 + (int)s.s3t[d * ES_TCOLS + (int)s.srk[2 * slot]] +
                       (int)s.s4t[d * ES_WCOLS + (int)s.srk[2 * slot + 1]]);
+}
+__device__ __forceinline__ unsigned int es_change_present_v(const EsSmem& s, int d, int slot) {
+    unsigned int ga;
+    return es_change_present_v(s, d, slot, ga);
 }
 
 // change: day d goes to an ABSENT employee whose holiday mask is hol
@@ -527,6 +538,36 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmem& s, const EsConst
         // (weekend rows of s2t are zero)
         ds += (int)s.s2t[d1 * ES_CBINS + __popcll(m2 & s.wdm[d1])] + (int)s.s2t[d2 * ES_CBINS + __popcll(m1 & s.wdm[d2])];
         // totals (S3) unchanged; a weekend day and a weekday trade places (S4)
+        if (wd1 >= 5 && wd2 < 5) ds += (int)s.s4s[d1 * ES_WCOLS + (int)s.srk[2 * s2 + 1]];
+        if (wd2 >= 5 && wd1 < 5) ds += (int)s.s4s[d2 * ES_WCOLS + (int)s.srk[2 * s1 + 1]];
+    }
+    return ((unsigned)(0x8000 + dh) << 16) | (unsigned)(0x8000 + ds);
+}
+
+// The same value from pass A's table (s.ga must be complete): a swap is two simultaneous
+// transfers, day d1 -> e2 and day d2 -> e1; their tabulated gains/losses are exact except where
+// both days meet -- the H2/H3 pair (d1, d2) itself and the windows holding BOTH days, whose
+// counts do not change.
+__device__ __forceinline__ unsigned int es_swap_from_table(const EsSmem& s, int d1, int d2) {
+    const int s1 = s.dslot[d1], s2 = s.dslot[d2];
+    const unsigned int g12 = s.ga[d1 * s.ns + s2], g21 = s.ga[d2 * s.ns + s1];  // d1 -> e2, d2 -> e1
+    const unsigned int b1 = s.base[d1], b2 = s.base[d2];
+    int dh = (int)(g12 & 31u) + (int)(g21 & 31u) + (int)(b1 >> 16) + (int)(b2 >> 16) - 0x10000;
+    int ds = (int)((g12 >> 5) & 7u) + (int)((g21 >> 5) & 7u) + (int)(b1 & 0xffffu) + (int)(b2 & 0xffffu) - 0x10000;
+    if (d2 - d1 < 14) {
+        if ((s.part[d1] >> d2) & 1ull) dh -= 2;
+        const u64* q1 = s.eq + s1 * 4;
+        const u64* q2 = s.eq + s2 * 4;
+        const u64 both14 = s.cont14[d1] & s.cont14[d2];
+        if (both14)
+            dh += __popcll(q1[1] & both14) - __popcll(q1[0] & both14) + __popcll(q2[1] & both14) - __popcll(q2[0] & both14);
+        const u64 both7 = s.cont7[d1] & s.cont7[d2];
+        if (both7)
+            ds += __popcll(q1[3] & both7) - __popcll(q1[2] & both7) + __popcll(q2[3] & both7) - __popcll(q2[2] & both7);
+    }
+    const int wd1 = s.dwd[d1], wd2 = s.dwd[d2];
+    if (wd1 != wd2) {
+        ds += (int)((g12 >> 8) & 31u) + (int)((g21 >> 8) & 31u) - 32;  // the two S2 transfers (weekend rows are 0)
         if (wd1 >= 5 && wd2 < 5) ds += (int)s.s4s[d1 * ES_WCOLS + (int)s.srk[2 * s2 + 1]];
         if (wd2 >= 5 && wd1 < 5) ds += (int)s.s4s[d2 * ES_WCOLS + (int)s.srk[2 * s1 + 1]];
     }
@@ -584,7 +625,9 @@ __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, 
         for (int k = tid; k < nA; k += nt) {
             const int id = d * E + (int)s.semp[slot];
             if ((int)s.dslot[d] != slot) {
-                const unsigned int v = es_change_present_v(s, d, slot);
+                unsigned int ga;
+                const unsigned int v = es_change_present_v(s, d, slot, ga);
+                s.ga[d * s.ns + slot] = (uint16_t)ga;
                 const long long k2 = es_key(v, id);
                 key = k2 < key ? k2 : key;
                 if (DUMP) {
@@ -637,13 +680,14 @@ __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, 
             key = k2 < key ? k2 : key;
         }
     }
+    __syncthreads();  // pass A's table is complete
     {   // C
         const int n_change = D * E, n_swap = D * (D - 1) / 2;
         for (int r = tid; r < n_swap; r += nt) {
             const int dd = tri[r], d1 = dd >> 8, d2 = dd & 0xff;
             const int id = n_change + r;
             if (s.dslot[d1] != s.dslot[d2]) {
-                const unsigned int v = es_swap_v(s, K, d1, d2);
+                const unsigned int v = es_swap_from_table(s, d1, d2);
                 const long long k2 = es_key(v, id);
                 key = k2 < key ? k2 : key;
                 if (DUMP) {
