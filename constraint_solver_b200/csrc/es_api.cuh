@@ -1,5 +1,6 @@
 // C ABI for the employee-scheduling plug-in (included by cs_api.cu; shares its helpers).
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 
 #include "es_kernels.cuh"
@@ -305,6 +306,10 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin, "employee table too large for shared memory");
         const long long moves = (long long)D * E + (long long)D * (D - 1) / 2;
         h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : moves <= 32768 ? 128 : 256;
+        if (const char* t = std::getenv("CS_ES_THREADS")) {  // tuning knob: CTA size (32..256, multiple of 32)
+            const int v = std::atoi(t);
+            if (v >= 32 && v <= 256 && v % 32 == 0) h->threads = v;
+        }
         CU(cudaFuncSetAttribute(es_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         CU(cudaFuncSetAttribute(es_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->ref_mode = (cfg->flags & CS_ES_FLAG_REFERENCE_PROPOSER) != 0;
