@@ -305,7 +305,9 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         h->smem = es_smem_bytes(D, E);
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin, "employee table too large for shared memory");
         const long long moves = (long long)D * E + (long long)D * (D - 1) / 2;
-        h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : moves <= 32768 ? 128 : 256;
+        // per-day phases keep <= 64 threads busy between barriers, so wide CTAs mostly wait (measured: 128 beats 256
+        // by 6 % at 56 x 2000, 32 beats 64 by 10 % at 28 x 50)
+        h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : 128;
         if (const char* t = std::getenv("CS_ES_THREADS")) {  // tuning knob: CTA size (32..256, multiple of 32)
             const int v = std::atoi(t);
             if (v >= 32 && v <= 256 && v % 32 == 0) h->threads = v;
