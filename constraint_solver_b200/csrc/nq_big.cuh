@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) nqb_scan_kernel(NqBig b) {
 // ---------------------------------------------------------------------------------------------
 // Packed-window scan for big boards: the shared-memory fast scan of nq_packed.cuh with the byte
 // counters in global memory (L2-resident, gathers served by L1).  A CTA takes 128 consecutive
-// columns (8 warps x 16 column slots) so its warps sweep the same j chunks together and their
+// columns (NQBP_WARPS warps x NQBP_TI column slots) so its warps sweep the same j chunks together and their
 // adjacent 16-byte gather windows share L1 sectors; a lane owns 4 consecutive columns j.
 // Diagonal ids need 21 bits at n = 10^6, so the 16x2 attack test compares a low and a high half.
 // Identical integer value per move as nqb_scan_kernel (parity: cs_nq_neighbourhood_deltas runs
@@ -266,7 +266,11 @@ __global__ void nqb_pack_kernel(NqBig b) {
 #ifndef NQBP_TI_VALUE
 #define NQBP_TI_VALUE 8
 #endif
-constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = 8 * NQBP_TI;  // 8 warps x TI slots
+#ifndef NQBP_WARPS_VALUE
+#define NQBP_WARPS_VALUE 16
+#endif
+constexpr int NQBP_WARPS = NQBP_WARPS_VALUE;  // warps per CTA: they sweep the same j chunks and share gather sectors in L1
+constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = NQBP_WARPS * NQBP_TI;
 constexpr int NQBP_INF16 = 0x3fff, NQBP_BIAS = 128;
 
 // the lane-consecutive operand is read once per tile: keep it out of L1 so the gather windows
@@ -278,7 +282,7 @@ __device__ __forceinline__ unsigned int nqbp_ld_stream(const unsigned char* p) {
 }
 
 template <bool DUMP>
-__global__ void __launch_bounds__(256, 2) nqb_scan_packed_kernel(NqBig b) {
+__global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_packed_kernel(NqBig b) {
     if (*b.maxcount > (unsigned)NQBP_MAX_COUNT) return;  // a line too long for byte sums: nqb_scan_kernel runs
     constexpr int TI = NQBP_TI;
     __shared__ int s_group;
