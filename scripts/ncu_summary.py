@@ -27,6 +27,8 @@ KEEP = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__t_sector_hit_rate.pct",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "l1tex__m_l1tex2xbar_write_bytes.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
@@ -79,6 +81,23 @@ def main():
             derived["instructions_per_32_moves"] = f("smsp__inst_executed.sum") / per32
         if "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum" in out:
             derived["global_ld_sectors_per_32_moves"] = f("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum") / per32
+    # achieved bandwidths over the kernel's own duration (for the GB/s-against-peak comparison)
+    def _bytes(k):
+        v, u = out[k].split()[:2]
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+    def _secs(k):
+        v, u = out[k].split()[:2]
+        return float(v.replace(",", "")) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(u.rstrip("econd"), 1e-9)
+    try:
+        t = _secs("gpu__time_duration.sum")
+        derived["dram_GBps"] = (_bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")) / t / 1e9
+        if "l1tex__m_xbar2l1tex_read_bytes.sum" in out:
+            derived["l2_to_l1_GBps"] = _bytes("l1tex__m_xbar2l1tex_read_bytes.sum") / t / 1e9
+        if "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum" in out:
+            derived["smem_GBps_at_128B_per_wavefront"] = f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") * 128.0 / t / 1e9
+        derived["warp_occupancy_pct"] = f("sm__warps_active.avg.pct_of_peak_sustained_active")
+    except Exception as e:  # a metric missing from this capture
+        derived["bandwidth_note"] = f"not derived: {e}"
     out["derived"] = derived
     json.dump(out, open(args.out, "w"), indent=1)
     print(json.dumps(out, indent=1))
