@@ -82,6 +82,8 @@ struct EsParams {
 // DP = D rounded up to 4 sizes the per-day arrays.
 constexpr int ES_TCOLS = 12;  // distinct total-day values among present employees (sum <= 64 => <= 10)
 constexpr int ES_WCOLS = 8;   // distinct weekend-day values (0 included; sum <= 20 => <= 6)
+// layout of EsSmem::val: total-day values by rank | weekend values by rank | per weekday: counts in use | their number
+constexpr int ES_VAL_C2 = ES_TCOLS + ES_WCOLS, ES_VAL_N2 = ES_VAL_C2 + 5 * 12, ES_VAL_BYTES = ES_VAL_N2 + 8;
 struct EsSmem {
     u64* mask;          // [E]
     uint16_t* a;        // [stride]
@@ -103,7 +105,7 @@ struct EsSmem {
     u64* shol;          // [NS] its holiday mask
     uint16_t* semp;     // [NS] its employee index
     unsigned char* srk;    // [NS][2] rank of its total-day / weekend-day count among the values in use
-    unsigned char* val;    // [ES_TCOLS + ES_WCOLS] rank -> value (total days | weekend days)
+    unsigned char* val;    // [ES_VAL_BYTES] rank -> value lists (see ES_VAL_*)
     unsigned char* dwd;    // [DP] weekday of the day (0 = Monday)
     unsigned char* dslot;  // [DP] slot of the day's current employee
     unsigned char* dayb;   // [3][DP] per day, for its current employee: total, weekend, weekday count
@@ -147,7 +149,7 @@ __host__ __device__ inline EsLayout es_layout(int D, int E) {
     L.a = o;       o = es_align(o + (size_t)(D + 1) * 2, 8);
     L.semp = o;    o = es_align(o + (size_t)L.ns * 2, 8);
     L.srk = o;     o = es_align(o + (size_t)L.ns * 2, 8);
-    L.val = o;     o = es_align(o + ES_TCOLS + ES_WCOLS, 8);
+    L.val = o;     o = es_align(o + ES_VAL_BYTES, 8);
     L.dwd = o;     o += dp;
     L.dslot = o;   o += dp;
     L.dayb = o;    o += 3 * dp;
@@ -415,13 +417,21 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
             q[3] = p7[0] & p7[1] & ~p7[2] & v7;                 // count == 3
         }
     }
-    {   // rank -> value tables of the total / weekend counts in use (j-th set bit)
-        const int j = nt - 1 - tid;  // the last threads: the first ones are busy with first days
-        if (j < ES_TCOLS + ES_WCOLS) {
-            u64 bits = j < ES_TCOLS ? occT : (u64)occW;
-            const int r = j < ES_TCOLS ? j : j - ES_TCOLS;
+    // rank -> value lists of the total / weekend counts in use (j-th set bit), and per weekday the
+    // counts in use (0 first): the memo tables below are built for exactly these values
+    for (int q = nt - 1 - tid; q < ES_VAL_BYTES; q += nt) {  // the last threads first: the first ones hold first days
+        if (q < ES_TCOLS + ES_WCOLS) {
+            u64 bits = q < ES_TCOLS ? occT : (u64)occW;
+            const int r = q < ES_TCOLS ? q : q - ES_TCOLS;
             for (int k = 0; k < r; ++k) bits &= bits - 1;
-            s.val[j] = (unsigned char)(bits ? __ffsll((long long)bits) - 1 : 0xff);
+            s.val[q] = (unsigned char)(bits ? __ffsll((long long)bits) - 1 : 0xff);
+        } else if (q < ES_VAL_C2 + 5 * ES_CBINS) {
+            const int wd = (q - ES_VAL_C2) / ES_CBINS, r = (q - ES_VAL_C2) - wd * ES_CBINS;
+            unsigned int bits = (s.occ2[wd] & 0x7feu) | 1u;  // counts 1..10 in use, and 0 (a newcomer to the weekday)
+            for (int k = 0; k < r; ++k) bits &= bits - 1;
+            s.val[q] = (unsigned char)(bits ? __ffs((int)bits) - 1 : 0xff);
+        } else if (q < ES_VAL_N2 + 5) {
+            s.val[q] = (unsigned char)__popc((s.occ2[q - ES_VAL_N2] & 0x7feu) | 1u);
         }
     }
     if (tid == 0) s.misc[ES_NSLOT] = __popcll(fm);
@@ -447,29 +457,39 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
         if (wd < 5) ds += es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], 0);
         s.baseW[d] = ((unsigned)(64 - lossH) << 15) | ((unsigned)(256 + ds) << 6) | (unsigned)d;
     }
-    for (int k = tid; k < D * ES_CBINS; k += nt) {
-        const int d = k / ES_CBINS, cn = k - d * ES_CBINS;
-        const int wd = s.dwd[d];
-        int v = 0;  // only counts some employee actually has on that weekday (and 0) are ever looked up
-        if (wd < 5 && cn < ES_CBINS - 1 && (cn == 0 || ((s.occ2[wd] >> cn) & 1u)))
-            v = es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], cn);
-        s.s2t[k] = (signed char)v;
+    // dense loops: only (day, value in use) pairs, so every lane of a warp has work
+    {
+        int nmax = 1;
+#pragma unroll
+        for (int wd = 0; wd < 5; ++wd) nmax = max(nmax, (int)s.val[ES_VAL_N2 + wd]);
+        for (int k = tid; k < D * nmax; k += nt) {
+            const int d = k / nmax, j = k - d * nmax;
+            const int wd = s.dwd[d];
+            if (wd >= 5) {
+                if (j == 0) s.s2t[d * ES_CBINS] = 0;  // weekend days: the only entry ever looked up
+            } else if (j < (int)s.val[ES_VAL_N2 + wd]) {
+                const int cn = s.val[ES_VAL_C2 + wd * ES_CBINS + j];
+                s.s2t[d * ES_CBINS + cn] = (signed char)es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], cn);
+            }
+        }
     }
-    for (int k = tid; k < D * ES_TCOLS; k += nt) {
-        const int d = k / ES_TCOLS, j = k - d * ES_TCOLS;
-        const int tn = s.val[j];
-        if (tn != 0xff) s.s3t[k] = (signed char)es_s3_delta(s, s.dayb[d], tn);
-    }
-    for (int k = tid; k < D * ES_WCOLS; k += nt) {
-        const int d = k / ES_WCOLS, j = k - d * ES_WCOLS;
-        const int wn = s.val[ES_TCOLS + j];
-        if (wn == 0xff) continue;
-        const int isw = s.dwd[d] >= 5 ? 1 : 0, wo = s.dayb[s.dp + d];
-        s.s4t[k] = (signed char)es_s4_delta(s, s.dayb[d], wo, isw, wn, true);
-        if (isw) {  // swap with a weekday of an employee holding wn weekend days: nobody joins or leaves
-            const int present = s.misc[ES_PRESENT];
-            const unsigned int occ = es_occ_move32(s.histW, occW, wo, wn, wo - 1, wn + 1);
-            s.s4s[k] = (signed char)(es_spread32(occ, present) - es_spread32(occW, present));
+    {
+        const int nT = __popcll(occT);
+        for (int k = tid; k < D * nT; k += nt) {
+            const int d = k / nT, j = k - d * nT;
+            s.s3t[d * ES_TCOLS + j] = (signed char)es_s3_delta(s, s.dayb[d], (int)s.val[j]);
+        }
+        const int nW = __popc(occW);
+        for (int k = tid; k < D * nW; k += nt) {
+            const int d = k / nW, j = k - d * nW;
+            const int wn = s.val[ES_TCOLS + j];
+            const int isw = s.dwd[d] >= 5 ? 1 : 0, wo = s.dayb[s.dp + d];
+            s.s4t[d * ES_WCOLS + j] = (signed char)es_s4_delta(s, s.dayb[d], wo, isw, wn, true);
+            if (isw) {  // swap with a weekday of an employee holding wn weekend days: nobody joins or leaves
+                const int present = s.misc[ES_PRESENT];
+                const unsigned int occ = es_occ_move32(s.histW, occW, wo, wn, wo - 1, wn + 1);
+                s.s4s[d * ES_WCOLS + j] = (signed char)(es_spread32(occ, present) - es_spread32(occW, present));
+            }
         }
     }
     __syncthreads();
