@@ -42,6 +42,7 @@ struct NqBig {
     unsigned int* maxcount;           // [1] largest diagonal line count (set by nqb_pack_kernel)
     int ldb;
     int use_packed;                   // host: permutation board, n >= NQBP_MIN_N, not forced scalar
+    int seg;                          // chunks (of 128 columns j) per work unit of the packed scan
 };
 
 constexpr int NQBP_MIN_N = 256;
@@ -272,6 +273,8 @@ __global__ void nqb_pack_kernel(NqBig b) {
 constexpr int NQBP_WARPS = NQBP_WARPS_VALUE;  // warps per CTA: they sweep the same j chunks and share gather sectors in L1
 constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = NQBP_WARPS * NQBP_TI;
 constexpr int NQBP_INF16 = 0x3fff, NQBP_BIAS = 128;
+constexpr int NQBP_SEG = 64;  // default chunks (of 128 columns j) per work unit (NqBig::seg); measured at n = 10^6:
+                              // 512 -> 1.58e12, 256 -> 1.75e12, 128 -> 1.90e12, 64 -> 1.91e12, 32 -> 1.79e12 moves/s
 
 // the lane-consecutive operand is read once per tile: keep it out of L1 so the gather windows
 // (shared by the CTA's warps) stay resident
@@ -297,12 +300,30 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
     unsigned int best_i = 0xffffffffu;
     unsigned long long pairs = 0;
 
+    // Work unit = (column group, segment of NQBP_SEG chunks of its j sweep), claimed from one
+    // counter in segment-major order.  A unit reports its own best (value, column); the min over
+    // units of that pair is the min over the whole slice, so nothing else has to be combined.
+    // Segments keep the early (long-sweep) partitions of a multi-GPU split from running in a few
+    // coarse waves.
+    const int n_chunks_all = (n + NQBP_CHUNK - 1) / NQBP_CHUNK;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_group = (int)atomicAdd(b.tile_counter, 1u);
         __syncthreads();
-        const int g = s_group;
-        if (g >= g_count) break;
+        int g = s_group, seg = 0;
+        bool none = false;
+        for (;;) {  // segment seg exists for the groups whose sweep is longer than seg * b.seg chunks
+            int gs = n_chunks_all - seg * b.seg - g_first;
+            gs = gs < 0 ? 0 : (gs > g_count ? g_count : gs);
+            if (gs == 0) {
+                none = true;
+                break;
+            }
+            if (g < gs) break;
+            g -= gs;
+            ++seg;
+        }
+        if (none) break;
         const int i0 = (g_first + g) * NQBP_GROUP + w * TI;
         if (i0 >= b.i_end || i0 + TI <= b.i_begin || i0 >= n - 1) continue;
         const int jbase = i0 & ~(NQBP_CHUNK - 1);
@@ -325,7 +346,7 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
                 uh |= (unsigned)((2 * ((idu >> 15) & 0x7fff)) & 0xffff) << (16 * h);
                 wl |= (unsigned)((2 * (idw & 0x7fff)) & 0xffff) << (16 * h);
                 wh |= (unsigned)((2 * ((idw >> 15) & 0x7fff)) & 0xffff) << (16 * h);
-                if (lane == 0 && i >= b.i_begin && i < b.i_end && i < n - 1) pairs += (unsigned long long)(n - 1 - i);
+                if (lane == 0 && seg == 0 && i >= b.i_begin && i < b.i_end && i < n - 1) pairs += (unsigned long long)(n - 1 - i);
             }
             NUl[p] = ~ul;  // x ^ ~y == ~(x ^ y): equal halves give 0xFFFF
             NUh[p] = ~uh;
@@ -410,11 +431,18 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
             }
         };
 
-        chunk(0, true);  // the chunk holding the tile: needs the j > i mask
         const int dj_full = (n & ~(NQBP_CHUNK - 1)) - jbase;  // end of the full chunks
-        int dj = NQBP_CHUNK;
-        for (; dj < dj_full; dj += NQBP_CHUNK) chunk(dj, false);
-        if (jbase + dj < n) chunk(dj, true);
+        const int span = n_chunks_all * NQBP_CHUNK - jbase;    // the whole sweep, partial last chunk included
+        int dj = seg * b.seg * NQBP_CHUNK;
+        int dj_hi = dj + b.seg * NQBP_CHUNK;
+        dj_hi = dj_hi < span ? dj_hi : span;
+        if (dj == 0) {
+            chunk(0, true);  // the chunk holding the tile: needs the j > i mask
+            dj = NQBP_CHUNK;
+        }
+        const int full_end = dj_hi < dj_full ? dj_hi : dj_full;
+        for (; dj < full_end; dj += NQBP_CHUNK) chunk(dj, false);
+        if (dj < dj_hi) chunk(dj, true);  // the partial last chunk: needs the j < n mask
 
 #pragma unroll
         for (int p = 0; p < TI / 2; ++p)

@@ -1,6 +1,7 @@
 // Host side of the big-board (global-memory, partitionable) n-queens path; included by
 // cs_api.cu after cs_nq_handle is defined.
 #pragma once
+#include <cstdlib>
 
 namespace {
 
@@ -58,6 +59,11 @@ void nqb_alloc(cs_nq_handle* h) {
     CU(cudaMalloc(&b.cb, (size_t)b.n_pad + 128));
     CU(cudaMemset(b.cb, 0, (size_t)b.n_pad + 128));
     b.use_packed = 0;
+    b.seg = NQBP_SEG;
+    if (const char* e = std::getenv("CS_NQB_SEG")) {  // tuning / test knob: work-unit length in chunks
+        const int v = std::atoi(e);
+        if (v >= 1) b.seg = v;
+    }
     CU(cudaMalloc(&b.R, (size_t)b.n_pad * 4));
     CU(cudaMalloc(&b.D1, (size_t)b.ld * 4));
     CU(cudaMalloc(&b.D2, (size_t)b.ld * 4));

@@ -218,7 +218,46 @@ def test_packed_global_scan_equals_oracle_and_scalar_scan():
                 assert orc.nq_score(r) == int(s)
 
 
+def test_packed_global_scan_short_work_units(monkeypatch):
+    """CS_NQB_SEG=3: every column group's j sweep is cut into 3-chunk work units (the multi-GPU
+    load-balancing path); deltas and trajectories must not change."""
+    monkeypatch.setenv("CS_NQB_SEG", "3")
+    rng = np.random.default_rng(12)
+    for n in (257, 400, 641):
+        rows = np.ascontiguousarray(rng.permutation(n), dtype=np.int64)
+        with cs.NQueensChains(n, 1, force_global=True) as e:
+            e.set_chains(rows)
+            assert np.array_equal(e.neighbourhood_deltas(0), orc.nq_neighbourhood_deltas(rows, orc.SWAP))
+    start = orc.nq_init_perm(5, 0, 2000)
+    with cs.NQueensChains(2000, 1, trace_capacity=8, force_global=True) as a, \
+            cs.NQueensChains(2000, 1, trace_capacity=8) as c:
+        a.set_chains(start)
+        c.set_chains(start)
+        sa, sc = a.step(5), c.step(5)
+        assert sa.moves_scored == sc.moves_scored == 5 * 2000 * 1999 // 2
+        ma, ca, ta = a.trace(0)
+        mc, cc, tc = c.trace(0)
+        assert ta == tc and np.array_equal(ma, mc) and np.array_equal(ca, cc)
+    monkeypatch.delenv("CS_NQB_SEG")
+    _partitions_impl(seg="2")
+
+
 def test_packed_global_scan_partitions():
+    _partitions_impl(seg=None)
+
+
+def _partitions_impl(seg=None):
+    if seg is not None:
+        import os
+        os.environ["CS_NQB_SEG"] = seg
+    try:
+        _partitions_body()
+    finally:
+        if seg is not None:
+            os.environ.pop("CS_NQB_SEG", None)
+
+
+def _partitions_body():
     """5 partitions of a permutation board (packed scan per slice): min of the keys applied on
     every replica == the unpartitioned step; the slices cover the neighbourhood exactly once."""
     import torch
