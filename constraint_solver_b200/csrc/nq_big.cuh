@@ -273,6 +273,7 @@ __global__ void nqb_pack_kernel(NqBig b) {
 constexpr int NQBP_WARPS = NQBP_WARPS_VALUE;  // warps per CTA: they sweep the same j chunks and share gather sectors in L1
 constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = NQBP_WARPS * NQBP_TI;
 constexpr int NQBP_INF16 = 0x3fff, NQBP_BIAS = 128;
+static_assert(NQBP_GROUP == NQBP_CHUNK, "the work-unit map assumes one column group per j chunk");
 constexpr int NQBP_SEG = 64;  // default chunks (of 128 columns j) per work unit (NqBig::seg); measured at n = 10^6:
                               // 512 -> 1.58e12, 256 -> 1.75e12, 128 -> 1.90e12, 64 -> 1.91e12, 32 -> 1.79e12 moves/s
 
