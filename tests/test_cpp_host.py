@@ -128,3 +128,35 @@ def test_cpp_scheduling_driver_json(scheduling_exe, tmp_path):
     plain = subprocess.run([scheduling_exe], capture_output=True, text=True, timeout=600)
     assert plain.returncode == 0 and "result.score: ScheduleScore { hard_score: OrderedFloat(0.0)" in plain.stdout
     assert plain.stdout.count("employee: Employee { id:") >= 2
+
+
+@pytest.mark.gpu
+def test_cpp_multi_gpu_driver_single_process_nccl():
+    """examples/cpp/nqueens_multi_gpu.cpp: one process, one handle per GPU, NCCL on the library's
+    device pointers.  The partitioned scan must give the same trajectory on 1 and on all GPUs."""
+    import re
+    import shutil
+
+    import constraint_solver_b200 as cs
+
+    if shutil.which("make") is None or not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("needs make and nccl.h")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples", "cpp"), "nqueens_multi_gpu"])
+    exe = os.path.join(ROOT, "examples", "cpp", "nqueens_multi_gpu")
+    G = cs.device_count()
+
+    def run(*args):
+        out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        m = re.search(r"(\S+) n=(\d+) gpus=(\d+) steps=(\d+): (\S+) moves scored .* best score (-?\d+)", out.stdout)
+        assert m, out.stdout
+        return int(m.group(5)), int(m.group(6))
+
+    n, steps = 3000, 6
+    moves1, best1 = run("--partitioned", "--board-size", str(n), "--steps", str(steps), "--gpus", "1")
+    assert moves1 == steps * n * (n - 1) // 2
+    if G >= 2:
+        movesg, bestg = run("--partitioned", "--board-size", str(n), "--steps", str(steps), "--gpus", str(G))
+        assert (movesg, bestg) == (moves1, best1)
+    moves, best = run("--board-size", "500", "--chains", "64", "--steps", "4", "--exchange", "2", "--gpus", str(G))
+    assert moves == 4 * G * 64 * (500 * 499 // 2) and best >= 0
