@@ -140,6 +140,8 @@ SIGNATURES = {
     "cs_nq_enumerate": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_nq_neighbourhood_deltas": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_nq_set_window": (C.c_int32, [_VP, C.c_uint64]),
+    "cs_nq_set_chains_async": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "cs_nq_commit_chains": (C.c_int32, [_VP]),
     "cs_nq_step": (C.c_int32, [_VP, C.c_uint32, _P(CsStepStats)]),
     "cs_nq_local_search": (C.c_int32, [_VP, C.c_uint64, C.c_uint64, _P(CsStepStats)]),
     "cs_nq_get_best_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, _VP]),

@@ -43,6 +43,9 @@ struct ArgFail {
 struct StateFail {
     std::string msg;
 };
+struct Unsupported {
+    std::string msg;
+};
 
 template <typename H, typename F>
 int32_t guarded(H* h, F&& f) {
@@ -65,6 +68,9 @@ int32_t guarded(H* h, F&& f) {
     } catch (const StateFail& s) {
         h->err = s.msg;
         return CS_ERR_STATE;
+    } catch (const Unsupported& u) {
+        h->err = u.msg;
+        return CS_ERR_UNSUPPORTED;
     } catch (const std::bad_alloc&) {
         h->err = "host out of memory";
         return CS_ERR_OOM;
@@ -135,6 +141,13 @@ struct cs_nq_handle {
     unsigned long long* h_totals = nullptr;  // pinned [2]
     long long* d_stage = nullptr;
     size_t stage_elems = 0;
+    // double-buffered input staging (cs_nq_set_chains_async / cs_nq_commit_chains)
+    long long* d_stage_async = nullptr;
+    size_t stage_async_elems = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_upload = nullptr;
+    uint32_t async_first = 0, async_count = 0;
+    bool async_pending = false;
     int* d_bad = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;  // chain scores valid
@@ -197,6 +210,9 @@ void nq_free(cs_nq_handle* h) {
     cudaFree(h->d_totals);
     cudaFree(h->d_stats);
     cudaFree(h->d_stage);
+    cudaFree(h->d_stage_async);
+    if (h->ev_upload) cudaEventDestroy(h->ev_upload);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaFree(h->d_bad);
     cudaFree(h->d_ls_rng);
     if (h->is_big) {
@@ -515,6 +531,62 @@ extern "C" int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first, uint32_t co
         }
         nq_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
+        h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_nq_set_chains_async(cs_nq_handle* h, uint32_t first, uint32_t count,
+                                          const int64_t* rows) {
+    return guarded(h, [&] {
+        REQUIRE(rows, "rows is NULL");
+        nq_check_range(h, first, count);
+        if (h->is_big) throw Unsupported{"asynchronous staging is for the chain (shared-memory) path"};
+        if (h->async_pending) throw StateFail{"an upload is already pending: call cs_nq_commit_chains first"};
+        const size_t need = (size_t)count * h->cfg.n;
+        if (!h->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming));
+        }
+        if (h->stage_async_elems < need) {
+            cudaFree(h->d_stage_async);
+            h->d_stage_async = nullptr;
+            h->stage_async_elems = 0;
+            CU(cudaMalloc(&h->d_stage_async, need * sizeof(long long)));
+            h->stage_async_elems = need;
+        }
+        // the copy engine works while the handle's stream runs kernels; nothing on the handle's
+        // stream reads d_stage_async until cs_nq_commit_chains
+        CU(cudaMemcpyAsync(h->d_stage_async, rows, need * sizeof(long long), cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaEventRecord(h->ev_upload, h->copy_stream));
+        h->async_first = first;
+        h->async_count = count;
+        h->async_pending = true;
+    });
+}
+
+extern "C" int32_t cs_nq_commit_chains(cs_nq_handle* h) {
+    return guarded(h, [&] {
+        if (!h->async_pending) throw StateFail{"no pending upload: call cs_nq_set_chains_async first"};
+        const uint32_t first = h->async_first, count = h->async_count;
+        const size_t n = h->cfg.n;
+        h->async_pending = false;
+        CU(cudaStreamWaitEvent(h->stream, h->ev_upload, 0));
+        CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+        const long long total = (long long)count * h->n_pad;
+        const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        nq_pack_rows_kernel<<<grid, 256, 0, h->stream>>>(h->d_stage_async, h->d_rows + (size_t)first * h->n_pad,
+                                                         (int)n, h->n_pad, (int)count, h->d_bad);
+        CU(cudaGetLastError());
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemsetAsync(h->d_ls_rng + first, 0, (size_t)count * sizeof(unsigned long long), h->stream));
+        nq_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first, (int)count);
+        CU(cudaGetLastError());
+        nq_rescore(h, (int)first, (int)count);
+        if (!h->scored && !(first == 0 && count == h->cfg.n_chains)) nq_rescore(h, 0, (int)h->cfg.n_chains);
+        nq_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        REQUIRE(!bad, "row value outside [0, n)");
         h->scored = true;
     });
 }

@@ -152,6 +152,15 @@ class NQueensChains:
         self._check(self._lib.cs_nq_set_chains(self._h, first_chain, count, C.c_void_p(host_ptr)),
                     "cs_nq_set_chains")
 
+    def set_chains_async_ptr(self, host_ptr: int, count: int, first_chain: int = 0):
+        """start the H2D copy of `count` int64 boards at host_ptr (pinned) on the copy stream"""
+        self._check(self._lib.cs_nq_set_chains_async(self._h, first_chain, count, C.c_void_p(host_ptr)),
+                    "cs_nq_set_chains_async")
+
+    def commit_chains(self):
+        """wait for the pending upload, then validate / pack / reset / score like set_chains"""
+        self._check(self._lib.cs_nq_commit_chains(self._h), "cs_nq_commit_chains")
+
     def get_chains(self, first_chain: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n_chains - first_chain if count is None else count
         out = np.empty((count, self.n), dtype=np.int64)

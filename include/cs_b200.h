@@ -128,6 +128,17 @@ int32_t cs_nq_init_random(cs_nq_handle* h);
  * moves and the perturbation legally break the permutation, lib.rs:228,311-312). */
 int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first_chain, uint32_t count,
                          const int64_t* rows);
+/* Double-buffered input staging for a stream of batches (no reference equivalent; the wasm worker
+ * feeds one problem per message, web/employee-scheduling/src/worker.ts:8-22).  _async starts the
+ * host -> device copy of `count` solutions on the library's copy stream and returns at once
+ * (rows must stay valid and should be pinned until the commit); the copy overlaps whatever the
+ * handle is running (e.g. cs_nq_step on the previous batch).  _commit waits for the copy, then
+ * does what cs_nq_set_chains does (validate, pack, reset the chains' state, score).  One upload
+ * may be pending per handle (CS_ERR_STATE otherwise); chain path only (CS_ERR_UNSUPPORTED on the
+ * big-board path). */
+int32_t cs_nq_set_chains_async(cs_nq_handle* h, uint32_t first_chain, uint32_t count,
+                               const int64_t* rows);
+int32_t cs_nq_commit_chains(cs_nq_handle* h);
 int32_t cs_nq_get_chains(cs_nq_handle* h, uint32_t first_chain, uint32_t count, int64_t* rows);
 /* current score of every chain (maintained by delta, written by step/local_search/set) */
 int32_t cs_nq_get_scores(cs_nq_handle* h, int64_t* scores /* [n_chains] */);

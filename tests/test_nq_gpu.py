@@ -243,3 +243,40 @@ def test_max_smem_board_runs():
         assert e.score_full(0) == s0
         e.step(1)
         assert e.score_full(0) == int(e.scores()[0]) < s0
+
+
+def test_async_staging_equals_synchronous_set_chains():
+    """cs_nq_set_chains_async + cs_nq_commit_chains: a pipelined stream of batches gives exactly
+    what cs_nq_set_chains gives, the copy may overlap a running step, and misuse is refused."""
+    import torch
+
+    n, chains = 300, 24
+    rng = np.random.default_rng(3)
+    batches = [np.stack([rng.permutation(n) for _ in range(chains)]).astype(np.int64) for _ in range(3)]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    with cs.NQueensChains(n, chains, trace_capacity=4) as a, cs.NQueensChains(n, chains, trace_capacity=4) as b:
+        with pytest.raises(cs.CsError):
+            a.commit_chains()                               # nothing pending
+        a.set_chains_async_ptr(pinned[0].data_ptr(), chains)
+        with pytest.raises(cs.CsError):
+            a.set_chains_async_ptr(pinned[1].data_ptr(), chains)   # one pending upload per handle
+        for k in range(3):
+            a.commit_chains()
+            if k + 1 < 3:
+                a.set_chains_async_ptr(pinned[k + 1].data_ptr(), chains)   # overlaps the step below
+            sa = a.step(3)
+            b.set_chains(batches[k])
+            sb = b.step(3)
+            assert np.array_equal(a.get_chains(), b.get_chains()) and np.array_equal(a.scores(), b.scores())
+            assert sa.moves_scored == sb.moves_scored and sa.best_score == sb.best_score
+            for c in (0, chains - 1):
+                ma, ca, ta = a.trace(c)
+                mb, cb_, tb = b.trace(c)
+                assert ta == tb and np.array_equal(ma, mb) and np.array_equal(ca, cb_)
+        bad = torch.full((chains, n), n, dtype=torch.int64).pin_memory()   # row value out of range
+        a.set_chains_async_ptr(bad.data_ptr(), chains)
+        with pytest.raises(cs.CsError):
+            a.commit_chains()
+    with cs.NQueensChains(64, 1, force_global=True) as g:
+        with pytest.raises(cs.CsError):
+            g.set_chains_async_ptr(pinned[0].data_ptr(), 1)   # big-board path: unsupported
