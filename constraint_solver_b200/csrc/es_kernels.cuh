@@ -12,17 +12,22 @@
 //   H4_e = #{w : popc(m & W14<<w) > 3}                           (:318-327)
 //   S1_e = #{w : popc(m & W7<<w)  > 2}                           (:330-339)
 // so a move's delta on these terms is F(m') - F(m) over the (at most two) employees whose
-// mask changes, with the window loops restricted to windows that overlap a changed day.
-// Hot-loop formulation (es_prepare + es_change_delta / es_swap_delta): once per chain-step,
-// for every PRESENT employee (<= D of them) all sliding-window counts are computed at once by a
-// bit-sliced adder over the day mask, kept as "count == k" window-start masks
-// (EQ3_14, EQ4_14, EQ2_7, EQ3_7); per day d the terms that only depend on the day's current
-// employee are tabulated.  A candidate then needs three 64-bit popcounts for H2+H3, H4 and S1:
-//   gain of day d for employee e = popc(m_e & PART[d]) + popc(EQ3_14[e] & CONT14[d]) ...
-// where PART[d] = days paired with d by H2/H3 and CONT[d] = window starts whose window holds d.
+// mask changes.
+// Hot-loop formulation (es_tally -> es_prepare -> es_scan).  At most D
+// employees are PRESENT (hold a day); each gets a slot = rank of its first day, so every
+// per-step table is built by <= D threads and nothing loops over the employee table.  Per slot
+// all sliding-window counts are computed at once by a bit-sliced adder over the day mask and
+// kept as "count == k" window-start masks (EQ3_14, EQ4_14, EQ2_7, EQ3_7); per day d the terms
+// that only depend on the day's current employee are tabulated (base[d]).  A change candidate to
+// a present employee then needs three 64-bit popcounts for H2+H3, H4 and S1:
+//   gain of day d for slot s = popc(m_s & PART[d]) + popc(EQ3_14[s] & CONT14[d]) ...
+// where PART[d] = days paired with d by H2/H3 and CONT[d] = window starts whose window holds d;
+// a candidate to an ABSENT employee is baseW[d] plus its holiday bit; a swap is two such
+// transfers (pass A's gain table) corrected where both days meet.
 // S2 (weekday affinity, min over employees present on that weekday), S3 (max-min of total
 // days over PRESENT employees) and S4 (max-min of weekend days over present employees) are
-// kept as count histograms + occupancy bitsets, so min/max after a move are bit scans.
+// kept as count histograms + occupancy bitsets; their deltas depend on the receiver only through
+// a count in use, so they are memoised per (day, value in use) as closed-form occupancy moves.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

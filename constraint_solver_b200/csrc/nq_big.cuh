@@ -7,6 +7,11 @@
 // GPUs) and every replica applies the same winning move -- no state exchange.
 //
 // Same delta formulae and the same (delta, i, j) tie-break as nq_kernels.cuh.
+//
+// Two scans: nqb_scan_kernel (u32 counters, any board) and nqb_scan_packed_kernel (byte counters
+// in 8 byte-shifted copies rebuilt per step, 16x2 SIMD, segment-major work units; permutation
+// boards with n >= 256 and no line above 62 queens -- decided on the device, the scalar scan
+// answers otherwise).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
