@@ -51,7 +51,7 @@ struct NqBig {
 };
 
 constexpr int NQBP_MIN_N = 256;
-constexpr int NQBP_COPIES = 8;      // byte shifts 0..7: any 8-counter window is one aligned 64-bit word
+constexpr int NQBP_COPIES = 16;     // byte shifts 0..15: any 16-counter window is one aligned 128-bit word
 constexpr int NQBP_MAX_COUNT = 62;   // four byte counters + slack stay below 256 (as nq_packed.cuh)
 __host__ __device__ inline int nqb_ldb(int n_pad) { return (2 * n_pad + 256 + 15) & ~15; }
 __host__ __device__ inline int nqb_ld(int n_pad) { return nqb_ldb(n_pad) + 64; }
@@ -235,33 +235,36 @@ __global__ void __launch_bounds__(256) nqb_scan_kernel(NqBig b) {
 // counters in global memory (L2-resident, gathers served by L1).  A CTA takes 128 consecutive
 // columns (NQBP_WARPS warps x NQBP_TI column slots) so its warps sweep the same j chunks together and their
 // adjacent 16-byte gather windows share L1 sectors; a lane owns 4 consecutive columns j.
-// Diagonal ids need 21 bits at n = 10^6, so the 16x2 attack test compares a low and a high half.
+// Diagonal ids need 21 bits at n = 10^6: the 16x2 attack test compares the low 15 bits and a rare
+// exact pass repairs the aliases (low halves equal, ids different).
 // Identical integer value per move as nqb_scan_kernel (parity: cs_nq_neighbourhood_deltas runs
 // THIS scan with the dump flag whenever the board qualifies).
 
-// u32 counters -> the eight byte-shifted copies of both arrays, and the largest line count
+// u32 counters -> the NQBP_COPIES byte-shifted copies of both arrays, and the largest line count
 __global__ void nqb_pack_kernel(NqBig b) {
     const int ldb = b.ldb;
     unsigned int mx = 0;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ldb / 8;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < ldb / 16;
          k += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(8 * k);
+        const int y = (int)(16 * k);
 #pragma unroll
         for (int arr = 0; arr < 2; ++arr) {
             const unsigned int* __restrict__ D = arr ? b.D2 : b.D1;
-            unsigned int d[15];
+            unsigned int d[16 + NQBP_COPIES - 1];
 #pragma unroll
-            for (int t = 0; t < 15; ++t) {
+            for (int t = 0; t < 16 + NQBP_COPIES - 1; ++t) {
                 d[t] = (y + t < b.ld) ? D[y + t] : 0u;
                 mx = max(mx, d[t]);
                 d[t] &= 0xffu;
             }
 #pragma unroll
             for (int c = 0; c < NQBP_COPIES; ++c) {
-                uint2 v;
+                uint4 v;
                 v.x = d[c] | (d[c + 1] << 8) | (d[c + 2] << 16) | (d[c + 3] << 24);
                 v.y = d[c + 4] | (d[c + 5] << 8) | (d[c + 6] << 16) | (d[c + 7] << 24);
-                *(uint2*)(b.Q + (size_t)(NQBP_COPIES * arr + c) * ldb + y) = v;
+                v.z = d[c + 8] | (d[c + 9] << 8) | (d[c + 10] << 16) | (d[c + 11] << 24);
+                v.w = d[c + 12] | (d[c + 13] << 8) | (d[c + 14] << 16) | (d[c + 15] << 24);
+                *(uint4*)(b.Q + (size_t)(NQBP_COPIES * arr + c) * ldb + y) = v;
             }
         }
     }
@@ -270,10 +273,10 @@ __global__ void nqb_pack_kernel(NqBig b) {
 }
 
 #ifndef NQBP_TI_VALUE
-#define NQBP_TI_VALUE 8
+#define NQBP_TI_VALUE 16
 #endif
 #ifndef NQBP_WARPS_VALUE
-#define NQBP_WARPS_VALUE 16
+#define NQBP_WARPS_VALUE 8
 #endif
 constexpr int NQBP_WARPS = NQBP_WARPS_VALUE;  // warps per CTA: they sweep the same j chunks and share gather sectors in L1
 constexpr int NQBP_TI = NQBP_TI_VALUE, NQBP_TJ = 4, NQBP_CHUNK = 128, NQBP_GROUP = NQBP_WARPS * NQBP_TI;
@@ -335,10 +338,10 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
         const int jbase = i0 & ~(NQBP_CHUNK - 1);
 
         int pv1[TI], pv2[TI];
-        unsigned NUl[TI / 2], NUh[TI / 2], NWl[TI / 2], NWh[TI / 2], m[TI / 2];
+        unsigned NUl[TI / 2], NWl[TI / 2], m[TI / 2];
 #pragma unroll
         for (int p = 0; p < TI / 2; ++p) {
-            unsigned ul = 0, uh = 0, wl = 0, wh = 0;
+            unsigned ul = 0, wl = 0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int a = 2 * p + h, i = i0 + a;
@@ -349,15 +352,11 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
                 pv2[a] = q2off + x2 + (x2 & 3) * ldbm1 + 4 * lane + jbase;
                 const int idu = ri - i + n, idw = ri + i;  // diagonal ids, 0 <= id < 2^21 for real columns
                 ul |= (unsigned)((2 * (idu & 0x7fff)) & 0xffff) << (16 * h);
-                uh |= (unsigned)((2 * ((idu >> 15) & 0x7fff)) & 0xffff) << (16 * h);
                 wl |= (unsigned)((2 * (idw & 0x7fff)) & 0xffff) << (16 * h);
-                wh |= (unsigned)((2 * ((idw >> 15) & 0x7fff)) & 0xffff) << (16 * h);
                 if (lane == 0 && seg == 0 && i >= b.i_begin && i < b.i_end && i < n - 1) pairs += (unsigned long long)(n - 1 - i);
             }
             NUl[p] = ~ul;  // x ^ ~y == ~(x ^ y): equal halves give 0xFFFF
-            NUh[p] = ~uh;
             NWl[p] = ~wl;
-            NWh[p] = ~wh;
             m[p] = (unsigned)NQBP_INF16 * 0x10001u;
         }
         const int A1 = i0 + n - 1, A2 = i0;
@@ -390,30 +389,27 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
                 const int cj = (int)(c4 >> (8 * bb)) & 0xff;
                 // data-dependent windows over the 16 column slots (shared with the neighbouring warps)
                 const int t1 = A1 - rj, t2 = A2 + rj;
-                // copy (t & 7), 64-bit word (t & ~7): one sector per load
-                const unsigned char* g1 = Q + t1 + (t1 & 7) * ldbm1;
-                const unsigned char* g2 = Q + q2off + t2 + (t2 & 7) * ldbm1;
+                // copy (t & 15), 128-bit word (t & ~15): one sector per load, 16 column slots
+                const uint4 v1 = __ldg((const uint4*)(Q + t1 + (t1 & 15) * ldbm1));
+                const uint4 v2 = __ldg((const uint4*)(Q + q2off + t2 + (t2 & 15) * ldbm1));
                 unsigned X[TI / 4];
-#pragma unroll
-                for (int g8 = 0; g8 < TI / 8; ++g8) {
-                    const uint2 v1 = __ldg((const uint2*)(g1 + 8 * g8)), v2 = __ldg((const uint2*)(g2 + 8 * g8));
-                    X[2 * g8] = v1.x + v2.x + TP[bb][2 * g8];
-                    X[2 * g8 + 1] = v1.y + v2.y + TP[bb][2 * g8 + 1];
-                }
+                X[0] = v1.x + v2.x + TP[bb][0];
+                X[1] = v1.y + v2.y + TP[bb][1];
+                X[2] = v1.z + v2.z + TP[bb][2];
+                X[3] = v1.w + v2.w + TP[bb][3];
                 const unsigned kj = (unsigned)(7 + NQBP_BIAS - cj) * 0x10001u;
                 const int idu = rj - j + n, idw = rj + j;
                 const unsigned ul = (unsigned)(2 * (idu & 0x7fff)) * 0x10001u;
-                const unsigned uh = (unsigned)(2 * ((idu >> 15) & 0x7fff)) * 0x10001u;
                 const unsigned wl = (unsigned)(2 * (idw & 0x7fff)) * 0x10001u;
-                const unsigned wh = (unsigned)(2 * ((idw >> 15) & 0x7fff)) * 0x10001u;
+                unsigned hit = 0;  // some slot's LOW id half matched: a real attack or a 2^-15 alias
 #pragma unroll
                 for (int p = 0; p < TI / 2; ++p) {
                     const unsigned x16 = __byte_perm(X[p / 2], 0u, (p & 1) ? 0x4342 : 0x4140);
                     unsigned y = x16 + kj;
-                    // same diagonal <=> low and high id halves both equal: XNORs all ones (-1), else <= 0xFFFD (-3)
-                    const unsigned eu = (ul ^ NUl[p]) & (uh ^ NUh[p]);
-                    const unsigned ew = (wl ^ NWl[p]) & (wh ^ NWh[p]);
-                    const unsigned a2 = __vimax3_u16x2(eu, ew, 0xFFFDFFFDu);
+                    // low 15 id bits equal: XNOR all ones (-1), else <= 0xFFFD (-3).  An alias (low halves
+                    // equal, ids different) makes this value 2 too HIGH; the exact pass below repairs it.
+                    const unsigned a2 = __vimax3_u16x2(ul ^ NUl[p], wl ^ NWl[p], 0xFFFDFFFDu);
+                    hit |= a2 ^ 0xFFFDFFFDu;
                     if (masked) {
                         const int ia = i0 + 2 * p;
                         unsigned pen = 0;
@@ -433,6 +429,33 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
                         }
                     }
                     m[p] = __viaddmin_s16x2(y, a2, m[p]);
+                }
+                if (hit) {  // rare (2 * TI / 2^15 per column j): redo this j with the full ids
+#pragma unroll
+                    for (int p = 0; p < TI / 2; ++p) {  // unrolled: m[] and X[] stay in registers
+                        const unsigned x16 = __byte_perm(X[p / 2], 0u, (p & 1) ? 0x4342 : 0x4140);
+                        unsigned y = x16 + kj, a2 = 0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = i0 + 2 * p + h;
+                            const int ri = (int)__ldg(rows + i);
+                            const bool att = (ri - i == rj - j) || (ri + i == rj + j);
+                            a2 |= (att ? 0xFFFFu : 0xFFFDu) << (16 * h);
+                            if (masked && !(j > i && j < n)) y = __vadd2(y, 0x4000u << (16 * h));
+                        }
+                        if (DUMP) {
+                            const unsigned z = __vadd2(y, a2);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int i = i0 + 2 * p + h;
+                                if (j > i && j < n && i >= b.i_begin && i < b.i_end) {
+                                    const int zz = (int)(short)((z >> (16 * h)) & 0xffff);
+                                    b.dump[nq_swap_index(n, i, j)] = 2ll * (long long)(zz - NQBP_BIAS - (int)cb[i]);
+                                }
+                            }
+                        }
+                        m[p] = __viaddmin_s16x2(y, a2, m[p]);  // exact <= the aliased value: the min repairs it
+                    }
                 }
             }
         };

@@ -118,7 +118,7 @@ void nqb_enqueue_scan(cs_nq_handle* h, bool perm, long long* dump) {
     b.use_packed = (perm && b.n >= NQBP_MIN_N && !(h->cfg.flags & CS_NQ_FLAG_SCALAR)) ? 1 : 0;
     nqb_compute_c_kernel<<<nqb_grid(h, b.n), 256, 0, h->stream>>>(b);
     if (b.use_packed) {  // byte copies + largest line count, then the packed scan (no-op if a line is too long)
-        nqb_pack_kernel<<<nqb_grid(h, b.ldb / 8), 256, 0, h->stream>>>(b);
+        nqb_pack_kernel<<<nqb_grid(h, b.ldb / 16), 256, 0, h->stream>>>(b);
         if (dump) nqb_scan_packed_kernel<true><<<h->sm_count * (16 / NQBP_WARPS), 32 * NQBP_WARPS, 0, h->stream>>>(b);
         else nqb_scan_packed_kernel<false><<<h->sm_count * (16 / NQBP_WARPS), 32 * NQBP_WARPS, 0, h->stream>>>(b);
         // the fallback below returns at once unless the packed scan declined; it needs a fresh tile counter
