@@ -27,6 +27,7 @@ struct cs_es_handle {
     EsStats* d_stats = nullptr;
     EsStats* h_stats = nullptr;
     unsigned long long* h_totals = nullptr;
+    EsChainState* h_states = nullptr;  // pinned [n_chains]: chain states for get_scores / get_status / best
     long long* d_stage64 = nullptr;  // device staging: employee ids <-> dense indices are converted on the device
     long long* d_ids = nullptr;      // [E] sorted employee ids
     int* d_bad = nullptr;
@@ -78,6 +79,7 @@ void es_free(cs_es_handle* h) {
     cudaFree(h->d_stats);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->h_totals) cudaFreeHost(h->h_totals);
+    if (h->h_states) cudaFreeHost(h->h_states);
     cudaFree(h->d_stage64);
     cudaFree(h->d_ids);
     cudaFree(h->d_bad);
@@ -211,12 +213,12 @@ void es_download(cs_es_handle* h, const uint16_t* src, uint32_t first, uint32_t 
     }
 }
 
-std::vector<EsChainState> es_states(cs_es_handle* h, uint32_t first, uint32_t count) {
-    std::vector<EsChainState> st(count);
-    CU(cudaMemcpyAsync(st.data(), h->d_st + first, count * sizeof(EsChainState),
+// chain states through the pinned staging buffer (valid until the next call on the handle)
+const EsChainState* es_states(cs_es_handle* h, uint32_t first, uint32_t count) {
+    CU(cudaMemcpyAsync(h->h_states, h->d_st + first, count * sizeof(EsChainState),
                        cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return st;
+    return h->h_states;
 }
 
 }  // namespace
@@ -336,6 +338,7 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         CU(cudaMalloc(&h->d_stats, sizeof(EsStats)));
         CU(cudaMallocHost(&h->h_stats, sizeof(EsStats)));
         CU(cudaMallocHost(&h->h_totals, 2 * sizeof(unsigned long long)));
+        CU(cudaMallocHost(&h->h_states, (size_t)cfg->n_chains * sizeof(EsChainState)));
         h->stage_chains = std::min<size_t>(nc, std::max<size_t>(1, (size_t)(64u << 20) / (h->stride * 8)));
         CU(cudaMalloc(&h->d_stage64, h->stage_chains * h->stride * sizeof(long long)));
         CU(cudaMalloc(&h->d_ids, (size_t)E * sizeof(long long)));
@@ -445,7 +448,7 @@ extern "C" int32_t cs_es_get_scores(cs_es_handle* h, int64_t* hard, int64_t* sof
     return guarded(h, [&] {
         REQUIRE(hard && soft, "hard/soft is NULL");
         auto st = es_states(h, 0, h->cfg.n_chains);
-        for (size_t k = 0; k < st.size(); ++k) {
+        for (size_t k = 0; k < h->cfg.n_chains; ++k) {
             hard[k] = st[k].hard;
             soft[k] = st[k].soft;
         }
@@ -456,7 +459,7 @@ extern "C" int32_t cs_es_get_status(cs_es_handle* h, uint32_t* status) {
     return guarded(h, [&] {
         REQUIRE(status, "status is NULL");
         auto st = es_states(h, 0, h->cfg.n_chains);
-        for (size_t k = 0; k < st.size(); ++k) status[k] = st[k].status;
+        for (size_t k = 0; k < h->cfg.n_chains; ++k) status[k] = st[k].status;
     });
 }
 
