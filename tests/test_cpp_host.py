@@ -21,7 +21,8 @@ ORCDIR = os.path.join(ROOT, "oracle")
 def _compile(src, out, with_oracle=False):
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, out)
-    deps = [src, os.path.join(ROOT, "include", "local_search_b200.hpp"), os.path.join(ROOT, "include", "cs_b200.h")]
+    deps = [src, os.path.join(ROOT, "include", "local_search_b200.hpp"), os.path.join(ROOT, "include", "cs_b200.h"),
+            os.path.join(ROOT, "examples", "cpp", "solver_context.hpp")]
     if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
         return exe
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), src,
@@ -113,8 +114,11 @@ def test_cpp_scheduling_driver_json(scheduling_exe, tmp_path):
            "employeeHolidays": [["2022-05-10", "2022-05-11"], [], ["2022-06-01"], [], [], [], []]}
     p = tmp_path / "in.json"
     p.write_text(json.dumps(inp))
-    out = subprocess.run([scheduling_exe, "--json", str(p), "--chains", "64"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([scheduling_exe, "--json", str(p), "--chains", "64", "--progress"], capture_output=True, text=True,
+                         timeout=600)
     assert out.returncode == 0, out.stderr
+    info = [json.loads(l) for l in out.stderr.splitlines() if l.startswith("{")]   # get_iteration_info per round
+    assert info and info[0] == {"current": 1, "total": 250} and [i["current"] for i in info] == list(range(1, len(info) + 1))
     res = json.loads(out.stdout)
     days = res["days_to_employees"]
     assert len(days) == 28 and days[0][0] == "Mon 2022-05-09" and days[-1][0] == "Sun 2022-06-05"
