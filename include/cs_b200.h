@@ -275,7 +275,8 @@ typedef struct cs_es_handle cs_es_handle;
 
 typedef struct cs_es_config {
     uint32_t n_days;         /* D = end_date - start_date + 1, 1..CS_ES_MAX_DAYS */
-    uint32_t n_employees;    /* E, 1..65535 */
+    uint32_t n_employees;    /* E >= 1; the per-chain day-mask table (8 B per employee) lives in shared memory,
+                              * so E <= ~26 000 on B200 (CS_ERR_INVALID_ARG beyond: "employee table too large") */
     uint32_t start_weekday;  /* weekday of start_date, 0 = Monday .. 6 = Sunday */
     uint32_t n_chains;
     uint32_t chain_offset;
