@@ -77,3 +77,33 @@ def test_product_package_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or fn == "Makefile":
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not bad.search(text), fn
+
+
+def test_rust_ffi_declarations_match_the_header():
+    """integration/rust/.../ffi.rs cannot be compiled here (no cargo/rustc), so at least keep it in
+    lock-step with include/cs_b200.h: every extern fn exists in the header with the same number
+    of arguments, and every #[repr(C)] struct lists the header's fields in the header's order."""
+    hdr = open(os.path.join(ROOT, "include", "cs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    rs = open(os.path.join(ROOT, "integration", "rust", "local-search-b200", "src", "ffi.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    c_fns = {m.group(1): [a for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+             for m in re.finditer(r"\b(cs_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)}
+    rs_fns = {m.group(1): [a for a in m.group(2).split(",") if a.strip()]
+              for m in re.finditer(r"pub fn (cs_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
+    assert len(rs_fns) >= 30
+    for name, args in rs_fns.items():
+        assert name in c_fns, f"ffi.rs declares {name}, which the header does not"
+        assert len(args) == len(c_fns[name]), (name, args, c_fns[name])
+    c_structs = {m.group(2): re.findall(r"\b([a-z_0-9]+)\s*(?:\[\d+\])?\s*;", m.group(1))
+                 for m in re.finditer(r"typedef struct \w+ \{(.*?)\}\s*(\w+)\s*;", hdr, flags=re.S)}
+    rs_structs = {m.group(1): re.findall(r"pub ([a-z_0-9]+)\s*:", m.group(2))
+                  for m in re.finditer(r"pub struct (cs_\w+)\s*\{(.*?)\}", rs, flags=re.S)}
+    checked = 0
+    for name, fields in rs_structs.items():
+        if name in c_structs:
+            assert fields == c_structs[name], (name, fields, c_structs[name])
+            checked += 1
+    assert checked >= 5
+    assert "ABI version %d" % cs.load().cs_abi_version() in open(
+        os.path.join(ROOT, "integration", "rust", "local-search-b200", "src", "ffi.rs")).read()
