@@ -213,6 +213,10 @@ enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8,
 constexpr unsigned int ES_W_PAD = 0x7fff0000u;  // larger than any packed absent-candidate value, no overflow on +hol
 
 // ------------------------------------------------------------------ histogram helpers
+// bit b of a 64-bit set; bin 64 (one employee holding all 64 days) has no bit -- it can only occur
+// with a single present employee, where the spread is 0 whatever the set says
+__device__ __forceinline__ u64 es_bit64(int b) { return b < 64 ? 1ull << b : 0ull; }
+
 // Occupancy bitset after one member leaves bin r0, one leaves r1 (r1 < 0: nobody), one enters
 // a0 (a0 < 0: nobody) and one enters a1.  hist holds the current member count per bin.
 __device__ __forceinline__ u64 es_occ_move(const uint16_t* hist, u64 occ, int r0, int r1, int a0, int a1) {
@@ -220,11 +224,11 @@ __device__ __forceinline__ u64 es_occ_move(const uint16_t* hist, u64 occ, int r0
     if (r1 >= 0) {
         const int same = (r1 == r0) ? 1 : 0;
         c0 -= same;
-        if ((int)hist[r1] - 1 - same <= 0) occ &= ~(1ull << r1);
+        if ((int)hist[r1] - 1 - same <= 0) occ &= ~es_bit64(r1);
     }
-    if (c0 <= 0) occ &= ~(1ull << r0);
-    if (a0 >= 0) occ |= 1ull << a0;
-    return occ | (1ull << a1);
+    if (c0 <= 0) occ &= ~es_bit64(r0);
+    if (a0 >= 0) occ |= es_bit64(a0);
+    return occ | es_bit64(a1);
 }
 __device__ __forceinline__ unsigned int es_occ_move32(const uint16_t* hist, unsigned int occ, int r0, int r1, int a0,
                                                       int a1) {
@@ -337,7 +341,7 @@ __device__ void es_tally(const EsSmem& s, const EsConst& K, const u64* __restric
         const int t = __popcll(m), w = __popcll(m & K.wkend);
         es_hist16_inc(s.hist2, (int)(s.histT - s.hist2) + t);
         es_hist16_inc(s.hist2, (int)(s.histW - s.hist2) + w);
-        atomicOr(s.occT, 1ull << t);
+        atomicOr(s.occT, es_bit64(t));
         atomicOr(s.occW, 1u << w);
         atomicAdd(&s.misc[ES_PRESENT], 1);
         atomicAdd(&s.misc[ES_SAME], t * (t - 1) / 2);  // day pairs held by one employee (identity swaps)
@@ -410,7 +414,7 @@ __device__ void es_prepare(const EsSmem& s, const EsConst& K, const u64* __restr
             s.semp[slot] = (uint16_t)e;
             s.smask[slot] = m;
             s.shol[slot] = hol[e];
-            s.srk[2 * slot] = (unsigned char)__popcll(occT & ((1ull << t) - 1ull));
+            s.srk[2 * slot] = (unsigned char)__popcll(occT & (es_bit64(t) - 1ull));
             s.srk[2 * slot + 1] = (unsigned char)__popc(occW & ((1u << w) - 1u));
             u64 p14[4], p7[3];
             es_window_planes<14, 4>(m, p14);
