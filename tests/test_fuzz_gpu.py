@@ -87,3 +87,24 @@ def test_nqueens_random_boards_all_three_scans():
                 dev = e.neighbourhood_deltas(0)
                 bad = np.nonzero(dev != ref)[0]
                 assert bad.size == 0, (case, n, kw, bad[:5], dev[bad[:5]], ref[bad[:5]])
+
+
+def test_scheduling_one_employee_holds_every_day():
+    """D = 64 with all days on one employee: total-days bin 64 has no bit in the 64-bit occupancy
+    set (present == 1 there); moves out of and back into that state must still be exact."""
+    for D, E in [(64, 2), (64, 5), (63, 3), (14, 2)]:
+        ids = np.arange(E, dtype=np.int64) + 10
+        start = np.full(D + 1, ids[0], dtype=np.int64)
+        near = start.copy()
+        near[D // 2] = ids[1]                      # one day away from the degenerate state
+        for rows in (start, near):
+            with cs.ScheduleChains(D, ids, start_weekday=3, holidays=[(int(ids[1]), 0)], trace_capacity=8) as e:
+                e.set_chains(rows)
+                ref_h, ref_s = _oracle_deltas(rows[:D], ids, 3, [(int(ids[1]), 0)])
+                dev_h, dev_s = e.neighbourhood_deltas(0)
+                assert np.array_equal(dev_h, ref_h) and np.array_equal(dev_s, ref_s), (D, E)
+                ref = orc.es_local_search(rows[:D], ids, 3, [(int(ids[1]), 0)], allow_no_improvement_for=2,
+                                          max_iterations=6, trace_cap=8)
+                e.local_search(2, 6)
+                mv, th, ts, total = e.trace(0)
+                assert total == ref["steps"] and np.array_equal(th, ref["trace_hard"]) and np.array_equal(ts, ref["trace_soft"])
