@@ -291,11 +291,20 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         }
         {   // swap r -> (d1 << 8 | d2), enumeration order d1 < d2 row-major; appended as u16
             const size_t n_swap = (size_t)D * (D - 1) / 2;
-            dayc.resize(3 * 64 + (n_swap + 3) / 4 + 1, 0ull);
+            const size_t words = (n_swap + 3) / 4 + 1;
+            dayc.resize(3 * 64 + 2 * words, 0ull);
             uint16_t* tri = (uint16_t*)(dayc.data() + 192);
             size_t r = 0;
             for (int d1 = 0; d1 < D; ++d1)
                 for (int d2 = d1 + 1; d2 < D; ++d2) tri[r++] = (uint16_t)((d1 << 8) | d2);
+            // the same pairs in SCAN order: pairs closer than 14 days (whose windows overlap and need the
+            // both-day corrections) first, so a warp's 32 swaps take the same path; move ids stay row-major
+            uint16_t* scan = (uint16_t*)(dayc.data() + 192 + words);
+            r = 0;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int d1 = 0; d1 < D; ++d1)
+                    for (int d2 = d1 + 1; d2 < D; ++d2)
+                        if ((d2 - d1 < 14) == (pass == 0)) scan[r++] = (uint16_t)((d1 << 8) | d2);
         }
         std::vector<u64> hol(E, 0ull);
         for (uint64_t k = 0; k < n_hol; ++k) {

@@ -712,9 +712,10 @@ __device__ __forceinline__ long long es_scan(const EsSmem& s, const EsConst& K, 
     __syncthreads();  // pass A's table is complete
     {   // C
         const int n_change = D * E, n_swap = D * (D - 1) / 2;
+        const uint16_t* __restrict__ scan = tri + ((n_swap + 3) / 4 + 1) * 4;  // near pairs first (host-built)
         for (int r = tid; r < n_swap; r += nt) {
-            const int dd = tri[r], d1 = dd >> 8, d2 = dd & 0xff;
-            const int id = n_change + r;
+            const int dd = scan[r], d1 = dd >> 8, d2 = dd & 0xff;
+            const int id = n_change + es_tri_index(D, d1, d2);
             if (s.dslot[d1] != s.dslot[d2]) {
                 const unsigned int v = es_swap_from_table(s, d1, d2);
                 const long long k2 = es_key(v, id);
