@@ -139,6 +139,7 @@ SIGNATURES = {
     "cs_nq_eval_moves": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, C.c_uint64, _VP]),
     "cs_nq_enumerate": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_nq_neighbourhood_deltas": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
+    "cs_nq_band_deltas": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_nq_set_window": (C.c_int32, [_VP, C.c_uint64]),
     "cs_nq_set_chains_async": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
     "cs_nq_commit_chains": (C.c_int32, [_VP]),

@@ -82,6 +82,14 @@ int32_t guarded(H* h, F&& f) {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// The dynamic shared-memory opt-in is a per-function, per-device attribute (not per handle): always
+// raise it to the device's opt-in maximum, so handles of different sizes never lower each other's
+// limit and concurrent creates write the same value.
+template <typename K>
+void allow_max_smem(K kernel, const cudaDeviceProp& prop) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+}
+
 }  // namespace
 
 #include "ils_api.cuh"
@@ -300,7 +308,9 @@ void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
     }
 }
 
-void nq_upload(cs_nq_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
+// Returns true when some row value was outside [0, n): such rows are stored as 0, so the caller can
+// (and must) bring the chains' state in line with what is stored BEFORE reporting the error.
+bool nq_upload(cs_nq_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
     const size_t n = h->cfg.n;
     const size_t per = h->stage_elems / n;  // chains per staging pass
     CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
@@ -321,7 +331,7 @@ void nq_upload(cs_nq_handle* h, uint32_t first, uint32_t count, const int64_t* r
     int bad = 0;
     CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    REQUIRE(!bad, "row value outside [0, n)");
+    return bad != 0;
 }
 
 void nq_download(cs_nq_handle* h, const uint16_t* src, uint32_t first, uint32_t count,
@@ -404,12 +414,9 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin,
                 "board does not fit the shared-memory chain kernel on this device");
         h->threads = n <= 96 ? 128 : n <= 512 ? 256 : n <= 2048 ? 512 : 1024;
-        CU(cudaFuncSetAttribute(nq_step_kernel<NQ_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)h->smem));
-        CU(cudaFuncSetAttribute(nq_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)h->smem));
-        CU(cudaFuncSetAttribute(nq_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)h->smem));
+        allow_max_smem(nq_step_kernel<NQ_TI>, prop);
+        allow_max_smem(nq_rescore_kernel, prop);
+        allow_max_smem(nq_eval_kernel, prop);
         // resident CTAs: as many as fit, so small boards run several chains per SM
         int per_sm = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nq_step_kernel<NQ_TI>,
@@ -422,8 +429,7 @@ extern "C" int32_t cs_nq_create(const cs_nq_config* cfg, cs_nq_handle** out) {
             const size_t a = nq_smem_bytes_v2(h->n_pad), c = nqc_smem_bytes(h->n_pad);
             h->smem_v2 = a > c ? a : c;
             REQUIRE(h->smem_v2 <= (size_t)prop.sharedMemPerBlockOptin, "packed layout does not fit");
-            CU(cudaFuncSetAttribute(nq_step_kernel_v2<NQ_TI>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_v2));
+            allow_max_smem(nq_step_kernel_v2<NQ_TI>, prop);
         }
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
@@ -514,12 +520,13 @@ extern "C" int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first, uint32_t co
         REQUIRE(rows, "rows is NULL");
         nq_check_range(h, first, count);
         if (h->is_big) {
-            nqb_upload(h, rows);
+            const bool bad = nqb_upload(h, rows);
             nqb_rebuild(h, true);
             h->scored = true;
+            REQUIRE(!bad, "row value outside [0, n) (stored as 0)");
             return;
         }
-        nq_upload(h, first, count, rows);
+        const bool bad = nq_upload(h, first, count, rows);
         CU(cudaMemsetAsync(h->d_ls_rng + first, 0, (size_t)count * sizeof(unsigned long long), h->stream));
         nq_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first,
                                                                           (int)count);
@@ -532,6 +539,8 @@ extern "C" int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first, uint32_t co
         nq_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
         h->scored = true;
+        // the chains now hold the input with out-of-range rows replaced by 0, consistently scored
+        REQUIRE(!bad, "row value outside [0, n) (stored as 0)");
     });
 }
 
@@ -586,8 +595,8 @@ extern "C" int32_t cs_nq_commit_chains(cs_nq_handle* h) {
         if (!h->scored && !(first == 0 && count == h->cfg.n_chains)) nq_rescore(h, 0, (int)h->cfg.n_chains);
         nq_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
-        REQUIRE(!bad, "row value outside [0, n)");
         h->scored = true;
+        REQUIRE(!bad, "row value outside [0, n) (stored as 0)");
     });
 }
 
@@ -773,6 +782,66 @@ extern "C" int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, i
     });
 }
 
+extern "C" int32_t cs_nq_band_deltas(cs_nq_handle* h, uint32_t chain, uint32_t i_begin, uint32_t i_end,
+                                     int64_t* delta, uint64_t cap, uint64_t* n_out) {
+    return guarded(h, [&] {
+        nq_check_range(h, chain, 1);
+        REQUIRE(n_out, "n_out is NULL");
+        if (!h->scored) throw StateFail{"no solution loaded"};
+        REQUIRE(h->cfg.neighbourhood == CS_NQ_SWAP, "column bands are defined for the swap neighbourhood");
+        const uint64_t n = h->cfg.n;
+        REQUIRE(i_begin <= i_end && i_end <= (n ? n - 1 : 0), "band outside [0, n-1]");
+        auto tri = [&](uint64_t x) { return x * n - x * (x + 1) / 2; };  // entries of columns < x
+        const uint64_t base = tri(i_begin), cnt = tri(i_end) - base;
+        *n_out = cnt;
+        if (!delta || cnt == 0) return;
+        REQUIRE(cap >= cnt, "delta buffer too small");
+        long long* d_dump = nullptr;
+        if (h->is_big) {
+            // the scan itself is restricted to the band (the partition range), and writes through a
+            // pointer shifted by the band's first index, so only the band is ever allocated
+            REQUIRE(h->parts == 1, "band dumps need an unpartitioned handle");
+            CU(cudaMalloc(&d_dump, cnt * sizeof(long long)));
+            const int ib = h->big.i_begin, ie = h->big.i_end;
+            try {
+                CU(cudaMemsetAsync(d_dump, 0x7f, cnt * sizeof(long long), h->stream));
+                h->big.i_begin = (int)i_begin;
+                h->big.i_end = (int)i_end;
+                nqb_enqueue_scan(h, nqb_is_perm(h), d_dump - (long long)base);
+                CU(cudaMemcpyAsync(delta, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+            } catch (...) {
+                h->big.i_begin = ib;
+                h->big.i_end = ie;
+                cudaFree(d_dump);
+                throw;
+            }
+            h->big.i_begin = ib;
+            h->big.i_end = ie;
+            cudaFree(d_dump);
+            return;
+        }
+        // shared-memory path: the production scan dumps the whole neighbourhood on the device (the
+        // band is a contiguous slice of the row-major enumeration); only the band crosses PCIe
+        const uint64_t all = n * (n - 1) / 2;
+        CU(cudaMalloc(&d_dump, all * sizeof(long long)));
+        try {
+            CU(cudaMemsetAsync(d_dump, 0x7f, all * sizeof(long long), h->stream));
+            NqParams p = nq_params(h, (int)chain, 1);
+            p.max_steps = 1;
+            p.dump = d_dump;
+            CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+            nq_launch_step(h, p, 1);
+            CU(cudaMemcpyAsync(delta, d_dump + base, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } catch (...) {
+            cudaFree(d_dump);
+            throw;
+        }
+        cudaFree(d_dump);
+    });
+}
+
 extern "C" int32_t cs_nq_set_window(cs_nq_handle* h, uint64_t window_size) {
     return guarded(h, [&] {
         REQUIRE(window_size >= 1, "window_size must be >= 1");
@@ -801,17 +870,19 @@ extern "C" int32_t cs_nq_local_search_one(cs_nq_handle* h, const int64_t* start,
     return guarded(h, [&] {
         REQUIRE(start, "start is NULL");
         if (h->is_big) {
-            nqb_upload(h, start);
+            const bool bad = nqb_upload(h, start);
             nqb_rebuild(h, true);
             h->scored = true;
+            REQUIRE(!bad, "row value outside [0, n) (stored as 0)");
             nqb_run(h, max_iterations, allow, 1, nullptr);
             if (best) nqb_download(h, h->d_best_rows32, best);
         } else {
-            nq_upload(h, 0, 1, start);
+            const bool bad = nq_upload(h, 0, 1, start);
             nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, 0, 1);
             CU(cudaGetLastError());
             nq_rescore(h, 0, h->scored ? 1 : (int)h->cfg.n_chains);
             h->scored = true;
+            REQUIRE(!bad, "row value outside [0, n) (stored as 0)");
             nq_run(h, 0, 1, max_iterations, allow, 1, nullptr);
             if (best) nq_download(h, h->d_best_rows, 0, 1, best);
         }
@@ -886,14 +957,18 @@ extern "C" int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain,
         nq_check_range(h, chain, 1);
         REQUIRE(d_rows_u16, "d_rows_u16 is NULL");
         REQUIRE(!h->is_big, "not available on the big-board path");
-        CU(cudaMemcpyAsync(h->d_rows + (size_t)chain * h->n_pad, d_rows_u16,
-                           (size_t)h->cfg.n * sizeof(uint16_t), cudaMemcpyDeviceToDevice,
-                           h->stream));
+        CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+        nq_copy_rows_checked_kernel<<<(h->n_pad + 255) / 256, 256, 0, h->stream>>>(
+            (const uint16_t*)d_rows_u16, h->d_rows + (size_t)chain * h->n_pad, (int)h->cfg.n, h->n_pad, h->d_bad);
+        CU(cudaGetLastError());
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         nq_reset_state_kernel<<<1, 32, 0, h->stream>>>(h->d_st, (int)chain, 1);
         CU(cudaGetLastError());
         nq_rescore(h, (int)chain, 1);
         nq_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
+        REQUIRE(!bad, "row value outside [0, n) (stored as 0)");
     });
 }
 

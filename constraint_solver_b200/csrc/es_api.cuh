@@ -323,11 +323,11 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
             const int v = std::atoi(t);
             if (v >= 32 && v <= 256 && v % 32 == 0) h->threads = v;
         }
-        CU(cudaFuncSetAttribute(es_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        CU(cudaFuncSetAttribute(es_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        allow_max_smem(es_step_kernel<false>, prop);
+        allow_max_smem(es_step_kernel<true>, prop);
         h->ref_mode = (cfg->flags & CS_ES_FLAG_REFERENCE_PROPOSER) != 0;
-        CU(cudaFuncSetAttribute(es_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        CU(cudaFuncSetAttribute(es_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        allow_max_smem(es_rescore_kernel, prop);
+        allow_max_smem(es_eval_kernel, prop);
         int per_sm = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel<false>, h->threads, h->smem));
         if (per_sm < 1) per_sm = 1;

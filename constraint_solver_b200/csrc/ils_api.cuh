@@ -56,8 +56,12 @@ struct IlsHost {
         CU(cudaMalloc(&d_sum, sizeof(IlsSummary)));
         CU(cudaMallocHost(&h_sum, sizeof(IlsSummary)));
         perturb_smem = (size_t)(((len + 7) & ~7) + len) * sizeof(uint16_t);
-        CU(cudaFuncSetAttribute(ils_perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(perturb_smem > 48 * 1024 ? perturb_smem : 48 * 1024)));
+        {   // per function and device, not per handle: always the device's opt-in maximum (see allow_max_smem)
+            int dev = 0, optin = 0;
+            CU(cudaGetDevice(&dev));
+            CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            CU(cudaFuncSetAttribute(ils_perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        }
         ready = true;
     }
 

@@ -597,8 +597,8 @@ __global__ void nqb_pack_rows32_kernel(const long long* __restrict__ src, unsign
         unsigned v = 0;
         if (k < n) {
             const long long x = src[k];
-            if (x < 0 || x >= n) *bad = 1;
-            v = (unsigned)x;
+            if (x < 0 || x >= n) *bad = 1;  // flagged and stored as 0 (in bounds for the counter build)
+            else v = (unsigned)x;
         }
         dst[k] = v;
     }

@@ -231,7 +231,7 @@ void nqb_run(cs_nq_handle* h, unsigned long long max_steps, unsigned long long a
     }
 }
 
-void nqb_upload(cs_nq_handle* h, const int64_t* rows) {
+bool nqb_upload(cs_nq_handle* h, const int64_t* rows) {  // true: some row was out of range (stored as 0)
     const int n = (int)h->cfg.n;
     CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
     CU(cudaMemcpyAsync(h->d_stage, rows, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
@@ -241,7 +241,7 @@ void nqb_upload(cs_nq_handle* h, const int64_t* rows) {
     int bad = 0;
     CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    REQUIRE(!bad, "row value outside [0, n)");
+    return bad != 0;
 }
 
 void nqb_download(cs_nq_handle* h, const unsigned int* src, int64_t* rows) {

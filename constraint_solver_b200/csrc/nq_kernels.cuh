@@ -775,10 +775,26 @@ __global__ void nq_pack_rows_kernel(const long long* __restrict__ src, uint16_t*
         uint16_t v = 0;
         if (j < n) {
             const long long x = src[(long long)c * n + j];
+            // an out-of-range row is flagged AND stored as 0: whatever runs on these rows before the
+            // host sees the flag (the counter build indexes shared memory by row) stays in bounds
             if (x < 0 || x >= n) *bad = 1;
-            v = (uint16_t)x;
+            else v = (uint16_t)x;
         }
         dst[k] = v;
+    }
+}
+
+// u16 rows already on the device (elite broadcast target): same range check and clamp
+__global__ void nq_copy_rows_checked_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
+                                            int n, int n_pad, int* bad) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += gridDim.x * blockDim.x) {
+        uint16_t v = 0;
+        if (j < n) {
+            const uint16_t x = src[j];
+            if ((int)x >= n) *bad = 1;
+            else v = x;
+        }
+        dst[j] = v;
     }
 }
 

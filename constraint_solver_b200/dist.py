@@ -21,6 +21,13 @@ def device_view(ptr: int, shape, typestr: str, device) -> torch.Tensor:
     return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
 
 
+def _bind_to_torch_stream(eng) -> None:
+    """A handle's own stream is cudaStreamNonBlocking: it does not order against torch's current
+    stream, where the collectives run.  Put the engine's kernels on torch's current stream so
+    scan -> all_reduce -> apply (and step -> exchange) are ordered by the stream itself."""
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
 def owner_of(key: int, chains_per_rank: int):
     """(score, owning rank, local chain) of a packed best key."""
     gid = key & 0xFFFFFFFF
@@ -52,6 +59,7 @@ class BestExchange:
     def __init__(self, eng, dist, rank: int, world: int, chains_per_rank: int):
         self.eng, self.dist, self.rank, self.world = eng, dist, rank, world
         self.cpr = chains_per_rank
+        _bind_to_torch_stream(eng)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
         self.key = device_view(eng.best_key_device_ptr(), (1,), "<i8", dev)
@@ -81,6 +89,7 @@ class PartitionedBoard:
 
     def __init__(self, eng, dist, rank: int, world: int):
         self.eng, self.dist, self.rank, self.world = eng, dist, rank, world
+        _bind_to_torch_stream(eng)
         eng.set_partition(rank, world)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.key = device_view(eng.part_key_device_ptr(), (1,), "<i8", dev)

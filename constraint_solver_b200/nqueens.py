@@ -219,6 +219,16 @@ class NQueensChains:
                     "cs_nq_neighbourhood_deltas")
         return out[: n.value]
 
+    def band_deltas(self, i_begin: int, i_end: int, chain: int = 0) -> np.ndarray:
+        """Every candidate delta of columns [i_begin, i_end) from the production scan (swap)."""
+        n = C.c_uint64()
+        self._check(self._lib.cs_nq_band_deltas(self._h, chain, i_begin, i_end, None, 0, C.byref(n)),
+                    "cs_nq_band_deltas")
+        out = np.empty(max(n.value, 1), dtype=np.int64)
+        self._check(self._lib.cs_nq_band_deltas(self._h, chain, i_begin, i_end, _ptr(out), n.value, C.byref(n)),
+                    "cs_nq_band_deltas")
+        return out[: n.value]
+
     def set_window(self, window_size: int):
         self._check(self._lib.cs_nq_set_window(self._h, window_size), "cs_nq_set_window")
 

@@ -38,7 +38,7 @@ extern "C" {
 #define CS_ERR_STATE (-5)
 #define CS_ERR_UNSUPPORTED (-6)
 
-#define CS_ABI_VERSION 3
+#define CS_ABI_VERSION 4
 
 /* Largest board the shared-memory-resident chain kernels take (one CTA holds rows,
  * per-column line sums and both diagonal counter arrays in <= 227 KB). */
@@ -125,7 +125,9 @@ int32_t cs_nq_set_stream(cs_nq_handle* h, void* cuda_stream);
  * every chain := Fisher-Yates permutation of 0..n-1 from Philox (seed, chain_offset+k, INIT). */
 int32_t cs_nq_init_random(cs_nq_handle* h);
 /* Load `count` solutions (row-major int64 [count][n], values 0..n-1, any multiset -- change
- * moves and the perturbation legally break the permutation, lib.rs:228,311-312). */
+ * moves and the perturbation legally break the permutation, lib.rs:228,311-312).  A value outside
+ * [0, n) is CS_ERR_INVALID_ARG; the affected chains then hold the input with such values replaced
+ * by 0, consistently scored (nothing on the device ever indexes by an out-of-range row). */
 int32_t cs_nq_set_chains(cs_nq_handle* h, uint32_t first_chain, uint32_t count,
                          const int64_t* rows);
 /* Double-buffered input staging for a stream of batches (no reference equivalent; the wasm worker
@@ -164,6 +166,14 @@ int32_t cs_nq_enumerate(cs_nq_handle* h, uint32_t chain, cs_move* moves, uint64_
  * (c,v) row-major, n*n entries); identity -> INT64_MAX. */
 int32_t cs_nq_neighbourhood_deltas(cs_nq_handle* h, uint32_t chain, int64_t* delta,
                                    uint64_t cap, uint64_t* n_out);
+
+/* The same dump for a BAND of columns (swap neighbourhood): columns i in [i_begin, i_end), every
+ * j > i, band-relative enumeration order (entry of (i, j) = tri(i) - tri(i_begin) + j - i - 1 with
+ * tri(x) = x*n - x(x+1)/2).  This is how every-candidate parity is checked at sizes whose whole
+ * neighbourhood does not fit a buffer (n = 10^6: 5e11 candidates; a band of 8 columns is 8e6).  On
+ * the big-board path the production scan is restricted to the band, exactly as a partition is. */
+int32_t cs_nq_band_deltas(cs_nq_handle* h, uint32_t chain, uint32_t i_begin, uint32_t i_end,
+                          int64_t* delta, uint64_t cap, uint64_t* n_out);
 
 /* window_size of LocalSearch::new (local_search.rs:281); only reference mode truncates the
  * neighbourhood (default 5 * n, examples/nqueens/src/main.rs:130). */

@@ -1,4 +1,4 @@
-//! Raw bindings of include/cs_b200.h (ABI version 3; a subset of its entry points).  SOURCE ONLY -- never compiled here.
+//! Raw bindings of include/cs_b200.h (ABI version 4; a subset of its entry points).  SOURCE ONLY -- never compiled here.
 #![allow(non_camel_case_types, dead_code)]
 use std::os::raw::{c_char, c_void};
 

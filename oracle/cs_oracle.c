@@ -297,10 +297,26 @@ static int64_t es_window_violations(const int64_t* w, int64_t len, int64_t limit
 int orc_es_score_terms(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
                        const int64_t* hol_day, int64_t n_hol, int64_t out[8]) {
     for (int k = 0; k < 8; ++k) out[k] = 0;
-    /* H1 holidays, lib.rs:273-280 */
-    for (int64_t k = 0; k < n_hol; ++k) {
-        if (hol_day[k] < 0 || hol_day[k] >= D) return -1; /* unwrap() on None, :275 */
-        if (a[hol_day[k]] == hol_emp[k]) out[0] += 1;
+    /* H1 holidays, lib.rs:273-280.  The reference keeps them in a HashSet<Holiday> (lib.rs:255-259),
+     * so a duplicated (employee, day) entry counts ONCE: a day has one employee, hence at most one
+     * distinct matching pair per day -- a per-day flag de-duplicates exactly. */
+    {
+        unsigned char seen_small[512];
+        unsigned char* seen = D <= 512 ? seen_small : (unsigned char*)malloc((size_t)D);
+        memset(seen, 0, (size_t)(D > 0 ? D : 0));
+        int bad = 0;
+        for (int64_t k = 0; k < n_hol; ++k) {
+            if (hol_day[k] < 0 || hol_day[k] >= D) { /* unwrap() on None, :275 */
+                bad = 1;
+                break;
+            }
+            if (a[hol_day[k]] == hol_emp[k] && !seen[hol_day[k]]) {
+                seen[hol_day[k]] = 1;
+                out[0] += 1;
+            }
+        }
+        if (seen != seen_small) free(seen);
+        if (bad) return -1;
     }
     /* H2 consecutive days, lib.rs:286-292 */
     for (int64_t i = 0; i + 2 <= D; ++i)
@@ -1027,4 +1043,237 @@ int64_t orc_es_ils_ref(uint64_t seed, uint32_t chain, int64_t D, int start_weekd
     *best_soft = key < 0 ? -1 : key & 0xffffffffll;
     free(current);
     return r;
+}
+
+/* ------------------------------------------------------------------ O(1)-per-move delta scorer */
+static inline int d_less(int64_t d, int64_t a, int64_t b, int64_t D, int64_t A, int64_t B) {
+    if (A < 0) return 1;
+    if (d != D) return d < D;
+    if (a != A) return a < A;
+    return b < B;
+}
+
+/* NOT a reference function: the reference has no delta scoring (SURVEY.md "three facts", 1).  This
+ * is the checker's own counter formulation -- occupancy counters R[r], D1[c-r+n-1], D2[c+r] and the
+ * SURVEY 8(a2) formulae, written with all four shared-line correction terms spelled out (the
+ * device collapses them into one attack test; the two derivations are independent) -- so that
+ * every candidate of a benchmark-sized neighbourhood (5e7 at n = 10 000, a column band at
+ * n = 1e6) can be checked in seconds.  It is itself PROVEN against the literal clone + full
+ * re-score (orc_nq_neighbourhood_deltas) on every candidate of small boards, permutations and
+ * non-permutations, in tests/test_oracle_cpu.py; only then is it used as the big-size checker. */
+typedef struct {
+    int64_t n;
+    int32_t *R, *D1, *D2;
+} nq_counters;
+
+static void nq_counters_build(nq_counters* c, const int64_t* rows, int64_t n) {
+    c->n = n;
+    c->R = (int32_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+    c->D1 = (int32_t*)calloc((size_t)(2 * n + 1), sizeof(int32_t));
+    c->D2 = (int32_t*)calloc((size_t)(2 * n + 1), sizeof(int32_t));
+    for (int64_t j = 0; j < n; ++j) {
+        c->R[rows[j]] += 1;
+        c->D1[j - rows[j] + n - 1] += 1;
+        c->D2[j + rows[j]] += 1;
+    }
+}
+
+static void nq_counters_free(nq_counters* c) {
+    free(c->R);
+    free(c->D1);
+    free(c->D2);
+}
+
+/* SURVEY 8(a2), swap i<j with r_i != r_j (rows term is 0: the row multiset is unchanged):
+ *   d1 = (D1[i-rj] + D1[j-ri]) - (D1[i-ri] + D1[j-rj]) + 2 + [i-rj == j-ri] + [i-ri == j-rj]
+ *   d2 = the same on D2 with c+r indices;   delta = 2 * (d1 + d2)                                  */
+static inline int64_t nq_fast_swap_delta(const nq_counters* c, const int64_t* rows, int64_t i, int64_t j) {
+    const int64_t n = c->n, ri = rows[i], rj = rows[j], o = n - 1;
+    const int64_t d1 = (int64_t)c->D1[i - rj + o] + c->D1[j - ri + o] - c->D1[i - ri + o] - c->D1[j - rj + o] + 2 +
+                       (i - rj == j - ri) + (i - ri == j - rj);
+    const int64_t d2 = (int64_t)c->D2[i + rj] + c->D2[j + ri] - c->D2[i + ri] - c->D2[j + rj] + 2 +
+                       (i + rj == j + ri) + (i + ri == j + rj);
+    return 2 * (d1 + d2);
+}
+
+/* SURVEY 8(a2), change column c: r -> v, v != r */
+static inline int64_t nq_fast_change_delta(const nq_counters* c, const int64_t* rows, int64_t col, int64_t v) {
+    const int64_t n = c->n, r = rows[col], o = n - 1;
+    return 2 * (((int64_t)c->R[v] + c->D1[col - v + o] + c->D2[col + v]) -
+                ((int64_t)c->R[r] + c->D1[col - r + o] + c->D2[col + r]) + 3);
+}
+
+int64_t orc_nq_fast_band_deltas(const int64_t* rows, int64_t n, int kind, int64_t x_begin, int64_t x_end,
+                                int threads, int64_t* delta) {
+    nq_counters c;
+    nq_counters_build(&c, rows, n);
+    if (x_begin < 0) x_begin = 0;
+    if (x_end > n) x_end = n;
+    /* band-relative index: swap rows of the triangular enumeration, change rows of the n x n one */
+    const int64_t base = kind == ORC_NQ_SWAP ? x_begin * n - x_begin * (x_begin + 1) / 2 : x_begin * n;
+    int64_t total = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8) reduction(+ : total)
+    for (int64_t x = x_begin; x < x_end; ++x) {
+        if (kind == ORC_NQ_SWAP) {
+            int64_t* out = delta + (x * n - x * (x + 1) / 2 - base);
+            for (int64_t y = x + 1; y < n; ++y)
+                out[y - x - 1] = rows[x] == rows[y] ? INT64_MAX : nq_fast_swap_delta(&c, rows, x, y);
+            total += n - 1 - x;
+        } else {
+            int64_t* out = delta + (x * n - base);
+            for (int64_t y = 0; y < n; ++y)
+                out[y] = rows[x] == y ? INT64_MAX : nq_fast_change_delta(&c, rows, x, y);
+            total += n;
+        }
+    }
+    nq_counters_free(&c);
+    return total;
+}
+
+int64_t orc_nq_fast_argmin(const int64_t* rows, int64_t n, int kind, int threads, int64_t* best_delta,
+                           int64_t* best_a, int64_t* best_b) {
+    nq_counters c;
+    nq_counters_build(&c, rows, n);
+    int64_t bd = INT64_MAX, ba = -1, bb = -1, scored = 0;
+#pragma omp parallel num_threads(threads)
+    {
+        int64_t ld = INT64_MAX, la = -1, lb = -1, ls = 0;
+#pragma omp for schedule(dynamic, 8) nowait
+        for (int64_t x = 0; x < n; ++x) {
+            const int64_t y0 = kind == ORC_NQ_SWAP ? x + 1 : 0;
+            for (int64_t y = y0; y < n; ++y) {
+                if (kind == ORC_NQ_SWAP ? rows[x] == rows[y] : rows[x] == y) continue;
+                const int64_t d = kind == ORC_NQ_SWAP ? nq_fast_swap_delta(&c, rows, x, y)
+                                                      : nq_fast_change_delta(&c, rows, x, y);
+                ++ls;
+                /* (delta, a, b) order: first minimum in enumeration order */
+                if (d < ld || (d == ld && (x < la || (x == la && y < lb)))) {
+                    ld = d;
+                    la = x;
+                    lb = y;
+                }
+            }
+        }
+#pragma omp critical
+        {
+            scored += ls;
+            if (la >= 0 && (d_less(ld, la, lb, bd, ba, bb))) {
+                bd = ld;
+                ba = la;
+                bb = lb;
+            }
+        }
+    }
+    nq_counters_free(&c);
+    if (best_delta) *best_delta = bd;
+    if (best_a) *best_a = ba;
+    if (best_b) *best_b = bb;
+    return scored;
+}
+
+/* "CPU delta" courtesy baseline (SURVEY 8(d) "CPU reference timing" (ii)):
+ * the SAME counters + delta formulae as the GPU, one restart chain per host thread, full swap
+ * neighbourhood per step, steepest descent with the (delta, i, j) rule.  Clearly NOT the reference
+ * (which has no delta scoring); it isolates hardware from algorithm.  Returns candidates scored. */
+int64_t orc_nq_delta_baseline(uint64_t seed, int64_t n, int chains, int steps, int threads, int64_t* checksum) {
+    int64_t scored = 0, sum = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1) reduction(+ : scored, sum)
+    for (int k = 0; k < chains; ++k) {
+        int64_t* rows = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+        orc_nq_init_perm(seed, (uint32_t)k, n, rows);
+        nq_counters c;
+        nq_counters_build(&c, rows, n);
+        for (int s = 0; s < steps; ++s) {
+            int64_t bd = INT64_MAX, bi = -1, bj = -1;
+            for (int64_t i = 0; i + 1 < n; ++i)
+                for (int64_t j = i + 1; j < n; ++j) {
+                    if (rows[i] == rows[j]) continue;
+                    const int64_t d = nq_fast_swap_delta(&c, rows, i, j);
+                    ++scored;
+                    if (d < bd) {
+                        bd = d;
+                        bi = i;
+                        bj = j;
+                    }
+                }
+            if (bi < 0) break;
+            const int64_t ri = rows[bi], rj = rows[bj], o = n - 1;
+            c.D1[bi - ri + o]--; c.D2[bi + ri]--; c.D1[bj - rj + o]--; c.D2[bj + rj]--;
+            c.D1[bi - rj + o]++; c.D2[bi + rj]++; c.D1[bj - ri + o]++; c.D2[bj + ri]++;
+            rows[bi] = rj;
+            rows[bj] = ri;
+            sum += bd;
+        }
+        nq_counters_free(&c);
+        free(rows);
+    }
+    if (checksum) *checksum = sum;
+    return scored;
+}
+
+/* orc_nq_neighbourhood_deltas with the candidates spread over OpenMP threads (the same clone +
+ * full re-score per candidate; only the outer loop is parallel) */
+int64_t orc_nq_neighbourhood_deltas_mt(const int64_t* rows, int64_t n, int kind, int threads, int64_t* delta) {
+    const int64_t cur = orc_nq_score(rows, n);
+#pragma omp parallel num_threads(threads)
+    {
+        int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t x = 0; x < n; ++x) {
+            const int64_t y0 = (kind == ORC_NQ_SWAP) ? x + 1 : 0;
+            int64_t k = (kind == ORC_NQ_SWAP) ? x * n - x * (x + 1) / 2 : x * n;
+            for (int64_t y = y0; y < n; ++y, ++k) {
+                memcpy(cand, rows, sizeof(int64_t) * (size_t)n);
+                delta[k] = nq_apply(cand, kind, x, y) ? orc_nq_score(cand, n) - cur : INT64_MAX;
+            }
+        }
+        free(cand);
+    }
+    return kind == ORC_NQ_SWAP ? n * (n - 1) / 2 : n * n;
+}
+
+/* every candidate of the full scheduling neighbourhood, clone + full re-score each (OpenMP over
+ * candidates), in the device's enumeration order INCLUDING identities (INT64_MAX): D*E change
+ * entries (day outer, employee index inner) then D(D-1)/2 swap entries (d1 < d2 row-major) */
+int64_t orc_es_neighbourhood_deltas_mt(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                                       const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                                       int threads, int64_t* dhard, int64_t* dsoft) {
+    int64_t h0, s0;
+    if (orc_es_score(a, D, start_weekday, hol_emp, hol_day, n_hol, &h0, &s0)) return -1;
+    const int64_t n_change = D * E, n_swap = D * (D - 1) / 2;
+#pragma omp parallel num_threads(threads)
+    {
+        int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(D > 0 ? D : 1));
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t k = 0; k < n_change + n_swap; ++k) {
+            int kind;
+            int64_t x, y;
+            if (k < n_change) {
+                kind = ORC_ES_CHANGE;
+                x = k / E;
+                y = k % E;
+            } else {
+                kind = ORC_ES_SWAP;
+                int64_t r = k - n_change;
+                x = 0;
+                while (r >= D - 1 - x) {
+                    r -= D - 1 - x;
+                    ++x;
+                }
+                y = x + 1 + r;
+            }
+            memcpy(cand, a, sizeof(int64_t) * (size_t)D);
+            if (!es_apply(cand, employees, kind, x, y)) {
+                dhard[k] = INT64_MAX;
+                dsoft[k] = INT64_MAX;
+                continue;
+            }
+            int64_t h, s;
+            orc_es_score(cand, D, start_weekday, hol_emp, hol_day, n_hol, &h, &s);
+            dhard[k] = h - h0;
+            dsoft[k] = s - s0;
+        }
+        free(cand);
+    }
+    return n_change + n_swap;
 }

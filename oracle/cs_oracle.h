@@ -81,6 +81,23 @@ int64_t orc_nq_baseline_sample(const int64_t* rows, int64_t n, const int64_t* a,
                                const int64_t* b, int64_t n_moves, int threads,
                                int64_t* checksum);
 
+/* ---- checker-side O(1)-per-move delta scorer (NOT a reference function; see cs_oracle.c) ----
+ * Occupancy counters + the SURVEY 8(a2) formulae with all four shared-line corrections.  Proven
+ * against orc_nq_neighbourhood_deltas on every candidate of small boards (tests/test_oracle_cpu.py),
+ * then used to check every candidate of benchmark-sized neighbourhoods.
+ * Band: rows x in [x_begin, x_end) of the enumeration (swap: column i with all j > i; change: column
+ * c with all values), written band-relative in enumeration order; identity -> INT64_MAX. */
+int64_t orc_nq_fast_band_deltas(const int64_t* rows, int64_t n, int kind, int64_t x_begin, int64_t x_end,
+                                int threads, int64_t* delta);
+/* minimum of the whole neighbourhood by (delta, a, b); returns the non-identity candidates scored */
+int64_t orc_nq_fast_argmin(const int64_t* rows, int64_t n, int kind, int threads, int64_t* best_delta,
+                           int64_t* best_a, int64_t* best_b);
+/* "CPU delta" courtesy baseline: same counters + deltas as the GPU, one chain per thread, full swap
+ * neighbourhood + steepest descent per step.  Not the reference. */
+int64_t orc_nq_delta_baseline(uint64_t seed, int64_t n, int chains, int steps, int threads, int64_t* checksum);
+/* orc_nq_neighbourhood_deltas, candidates spread over OpenMP threads */
+int64_t orc_nq_neighbourhood_deltas_mt(const int64_t* rows, int64_t n, int kind, int threads, int64_t* delta);
+
 /* ---- employee scheduling ---- */
 /* Days since 1970-01-01 -> weekday 0=Mon..6=Sun (chrono NaiveDate::weekday restated). */
 int orc_weekday_from_days(int64_t days_since_epoch);
@@ -126,6 +143,12 @@ int64_t orc_es_baseline_sample(const int64_t* a, int64_t D, int start_weekday,
                                const int64_t* employees, int64_t E, int kind, const int64_t* x,
                                const int64_t* y, int64_t n_moves, int threads,
                                int64_t* checksum);
+
+/* every candidate of the full neighbourhood (clone + full re-score each, OpenMP over candidates) in
+ * the device's enumeration order including identities (INT64_MAX): D*E change, then D(D-1)/2 swap */
+int64_t orc_es_neighbourhood_deltas_mt(const int64_t* a, int64_t D, int start_weekday, const int64_t* hol_emp,
+                                       const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                                       int threads, int64_t* dhard, int64_t* dsoft);
 
 /* ---- iterated local search (iterated_local_search.rs:173-202; see cs_oracle.c) ---- */
 int64_t orc_nq_ils(uint64_t seed, uint32_t chain, int64_t n, int kind, uint64_t ls_max_iterations,

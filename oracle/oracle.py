@@ -50,6 +50,11 @@ def lib():
         _lib.orc_es_ils.restype = I64
         _lib.orc_es_local_search_ref.restype = I64
         _lib.orc_es_ils_ref.restype = I64
+        _lib.orc_nq_fast_band_deltas.restype = I64
+        _lib.orc_nq_fast_argmin.restype = I64
+        _lib.orc_nq_delta_baseline.restype = I64
+        _lib.orc_nq_neighbourhood_deltas_mt.restype = I64
+        _lib.orc_es_neighbourhood_deltas_mt.restype = I64
     return _lib
 
 
@@ -144,6 +149,56 @@ def nq_baseline_sample(rows, a, b, threads):
     return int(k), int(chk.value)
 
 
+def _threads(threads):
+    return int(threads) if threads else (os.cpu_count() or 1)
+
+
+def nq_band_size(n, x_begin, x_end, kind=SWAP):
+    if kind == SWAP:
+        tri = lambda x: x * n - x * (x + 1) // 2
+        return tri(x_end) - tri(x_begin)
+    return (x_end - x_begin) * n
+
+
+def nq_fast_band_deltas(rows, x_begin=0, x_end=None, kind=SWAP, threads=None):
+    """Checker-side O(1) delta scorer (counters + SURVEY 8(a2) formulae), band-relative order."""
+    r = _i64(rows)
+    n = len(r)
+    x_end = (n - 1 if kind == SWAP else n) if x_end is None else x_end
+    cnt = nq_band_size(n, x_begin, x_end, kind)
+    out = np.empty(max(cnt, 1), dtype=np.int64)
+    k = lib().orc_nq_fast_band_deltas(_p(r), I64(n), C.c_int(kind), I64(x_begin), I64(x_end),
+                                      C.c_int(_threads(threads)), _p(out))
+    assert k == cnt, (k, cnt)
+    return out[:cnt]
+
+
+def nq_fast_argmin(rows, kind=SWAP, threads=None):
+    """(delta, a, b, candidates scored) of the whole neighbourhood by the (delta, a, b) rule."""
+    r = _i64(rows)
+    d, a, b = I64(0), I64(0), I64(0)
+    k = lib().orc_nq_fast_argmin(_p(r), I64(len(r)), C.c_int(kind), C.c_int(_threads(threads)),
+                                 C.byref(d), C.byref(a), C.byref(b))
+    return int(d.value), int(a.value), int(b.value), int(k)
+
+
+def nq_delta_baseline(seed, n, chains, steps, threads=None):
+    chk = I64(0)
+    k = lib().orc_nq_delta_baseline(U64(seed), I64(n), C.c_int(chains), C.c_int(steps),
+                                    C.c_int(_threads(threads)), C.byref(chk))
+    return int(k), int(chk.value)
+
+
+def nq_neighbourhood_deltas_mt(rows, kind=SWAP, threads=None):
+    r = _i64(rows)
+    n = len(r)
+    cnt = n * (n - 1) // 2 if kind == SWAP else n * n
+    out = np.zeros(max(cnt, 1), dtype=np.int64)
+    k = lib().orc_nq_neighbourhood_deltas_mt(_p(r), I64(n), C.c_int(kind), C.c_int(_threads(threads)), _p(out))
+    assert k == cnt
+    return out[:cnt]
+
+
 # ---------------------------------------------------------------- employee scheduling
 def days_from_civil(y, m, d) -> int:
     return int(lib().orc_days_from_civil(I64(y), C.c_int(m), C.c_int(d)))
@@ -203,6 +258,22 @@ def es_eval_moves(a, employees, x, y, kind, start_weekday=0, holidays=None):
     if rc:
         raise ValueError("holiday outside the scored range")
     return dh[: len(x)], ds[: len(x)]
+
+
+def es_neighbourhood_deltas(a, employees, start_weekday=0, holidays=None, threads=None):
+    """(dhard, dsoft) of every candidate, device enumeration order, identities = INT64_MAX."""
+    a, employees = _i64(a), _i64(employees)
+    he, hd = _hol(holidays)
+    D, E = len(a), len(employees)
+    cnt = D * E + D * (D - 1) // 2
+    dh = np.zeros(max(cnt, 1), dtype=np.int64)
+    ds = np.zeros(max(cnt, 1), dtype=np.int64)
+    k = lib().orc_es_neighbourhood_deltas_mt(_p(a), I64(D), C.c_int(start_weekday), _p(he), _p(hd), I64(len(he)),
+                                             _p(employees), I64(E), C.c_int(_threads(threads)), _p(dh), _p(ds))
+    if k < 0:
+        raise ValueError("holiday outside the scored range")
+    assert k == cnt
+    return dh[:cnt], ds[:cnt]
 
 
 def es_local_search(a, employees, start_weekday=0, holidays=None,

@@ -35,7 +35,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_abi_version_and_status_strings():
     lib = cs.load()
-    assert lib.cs_abi_version() == 3
+    assert lib.cs_abi_version() == 4
     assert b"no CPU fallback" in lib.cs_status_string(L.CS_ERR_NO_DEVICE)
 
 

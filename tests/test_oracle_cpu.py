@@ -181,3 +181,117 @@ def test_scheduling_reference_proposer_restatement_against_a_python_rewrite():
         assert (int(ref["trace_hard"][steps]), int(ref["trace_soft"][steps])) == score
         steps += 1
     assert steps == ref["steps"] and np.array_equal(cur, ref["current"])
+
+
+# ---------------------------------------------------------------- round 2: the fast checker and the second scorer
+def test_fast_delta_scorer_equals_clone_and_full_rescore_on_every_candidate():
+    """The O(1) counter/delta scorer (the checker used at n = 10 000 ... 10^6) is itself proven
+    against the literal reference formulation -- clone + O(n^2) re-score of EVERY candidate --
+    on permutations, arbitrary multisets (change moves and the perturbation break the
+    permutation, nqueens lib.rs:228,311-312), all-equal and diagonal boards, n up to 400."""
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 4, 7, 16, 33, 64, 97, 150):
+        boards = [rng.permutation(n), rng.integers(0, n, n), np.zeros(n, dtype=np.int64), np.arange(n),
+                  np.arange(n)[::-1].copy()]
+        if n >= 4:
+            r = rng.permutation(n)
+            r[1] = r[n - 1]
+            boards.append(r)
+        for rows in boards:
+            for kind in (orc.SWAP, orc.CHANGE):
+                slow = orc.nq_neighbourhood_deltas(rows, kind)
+                assert np.array_equal(orc.nq_neighbourhood_deltas_mt(rows, kind), slow)
+                fast = orc.nq_fast_band_deltas(rows, kind=kind)
+                assert np.array_equal(fast, slow), (n, kind)
+    for n, make in ((400, lambda: rng.permutation(400)), (301, lambda: rng.integers(0, 301, 301))):
+        rows = make()
+        slow = orc.nq_neighbourhood_deltas_mt(rows, orc.SWAP)      # 8e4 candidates x 8e4 pair tests
+        assert np.array_equal(orc.nq_fast_band_deltas(rows), slow)
+        # bands tile the enumeration
+        cuts = [0, 1, 17, n // 2, n - 2, n - 1]
+        parts = [orc.nq_fast_band_deltas(rows, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert np.array_equal(np.concatenate(parts), slow)
+        # argmin by (delta, i, j) == first minimum of the enumeration
+        d, a, b, scored = orc.nq_fast_argmin(rows)
+        k = int(np.argmin(slow))
+        assert slow[k] == d and scored == int((slow != orc.INT64_MAX).sum())
+        assert k == a * n - a * (a + 1) // 2 + (b - a - 1)
+
+
+def test_cpu_delta_baseline_walks_the_oracle_trajectory():
+    n, steps = 60, 4
+    scored, chk = orc.nq_delta_baseline(5, n, 3, steps, threads=2)
+    want_scored, want_sum = 0, 0
+    for chain in range(3):
+        res = orc.nq_local_search(orc.nq_init_perm(5, chain, n), allow_no_improvement_for=10**9,
+                                  max_iterations=steps, trace_cap=steps)
+        s0 = orc.nq_score(orc.nq_init_perm(5, chain, n))
+        want_sum += int(res["trace_score"][-1]) - s0
+        want_scored += steps * n * (n - 1) // 2
+    assert (scored, chk) == (want_scored, want_sum)
+
+
+def test_duplicate_holiday_entries_count_once():
+    """The reference keeps holidays in a HashSet<Holiday> (lib.rs:255-259): a repeated (employee,
+    day) entry is one holiday.  (the oracle used to count it twice.)"""
+    a = [0, 1, 0, 1, 2, 2, 0]
+    once = orc.es_score_terms(a, 0, [(0, 0), (1, 3), (2, 4)])
+    twice = orc.es_score_terms(a, 0, [(0, 0), (0, 0), (1, 3), (2, 4), (1, 3), (0, 0)])
+    assert once.tolist() == twice.tolist() and int(once[0]) == 3
+    assert int(orc.es_score_terms(a, 0, [(0, 1), (0, 1)])[0]) == 0
+
+
+def _second_scorer_case(rng, D, E, wd_shift, holiday_heavy):
+    import datetime as dt
+
+    from es_second_scorer import ScheduleSolution, get_scored_solution
+
+    start = dt.date(2022, 5, 9) + dt.timedelta(days=int(wd_shift))   # 2022-05-09 is a Monday
+    ids = np.sort(rng.choice(np.arange(0, 3 * E + 5), size=E, replace=False)).astype(np.int64)
+    style = rng.integers(0, 4)
+    if style == 0:
+        a = ids[rng.integers(0, E, size=D + 1)]
+    elif style == 1:
+        a = ids[rng.integers(0, min(E, 3), size=D + 1)]               # few employees, long runs
+    elif style == 2:
+        a = ids[(np.arange(D + 1) + rng.integers(0, E)) % E]          # round robin
+    else:
+        a = ids[(rng.integers(0, E) + np.arange(D + 1) // int(rng.integers(1, 5))) % E]
+    nh = int(rng.integers(0, 3 * D * min(E, 4) + 1)) if holiday_heavy else int(rng.integers(0, E + 2))
+    hol = [(int(ids[rng.integers(0, E)]), int(rng.integers(0, D))) for _ in range(nh)]  # duplicates allowed
+    table = {}
+    for emp, day in hol:
+        table.setdefault(emp, set()).add(start + dt.timedelta(days=day))
+    sol = ScheduleSolution(start, start + dt.timedelta(days=D - 1), a.tolist())
+    return get_scored_solution(sol, table), orc.es_score(a[:D], start.weekday(), hol), (D, E, a.tolist(), hol)
+
+
+def test_c_oracle_against_the_independent_python_scorer_on_random_rotas():
+    """>= 1000 random rotas incl. D < 7, D < 14, D >= 64 (beyond the first device limit), single
+    employee, holiday-heavy and duplicate-holiday cases: (hard, soft) of the date-based Python
+    rewrite (tests/es_second_scorer.py, written from lib.rs:261-375) == the C oracle."""
+    rng = np.random.default_rng(20251018)
+    n = 0
+    shapes = [(1, 1), (2, 1), (3, 2), (6, 2), (7, 3), (8, 1), (9, 4), (13, 2), (14, 5), (15, 3), (21, 7),
+              (28, 50), (31, 7), (56, 20), (64, 9), (90, 11), (168, 30)]
+    for rep in range(62):
+        for D, E in shapes:
+            got, want, info = _second_scorer_case(rng, D, E, rng.integers(0, 7), rep % 3 == 0)
+            assert got == want, info
+            n += 1
+    assert n >= 1000
+
+
+def test_second_scorer_reproduces_the_committed_golden_vectors(golden_dir):
+    import datetime as dt
+
+    from es_second_scorer import ScheduleSolution, get_scored_solution
+
+    g = _load(golden_dir, "es_kat.json")
+    start = dt.date.fromisoformat(g["start_date"])
+    for case in g["cases"]:
+        table = {}
+        for emp, day in case["holidays"]:
+            table.setdefault(emp, set()).add(start + dt.timedelta(days=day))
+        sol = ScheduleSolution(start, start + dt.timedelta(days=len(case["a"]) - 1), case["a"])
+        assert get_scored_solution(sol, table) == (case["hard"], case["soft"])
