@@ -22,3 +22,16 @@ def philox4x32_10(seed: int, chain: int, purpose: int, counter: int):
 
 def device_count() -> int:
     return int(load().cs_device_count())
+
+
+MICROBENCH_SMEM_LDS32, MICROBENCH_SMEM_LDS128, MICROBENCH_L2_READ = 0, 1, 2
+
+
+def microbench(which: int, device: int = -1):
+    """Measured on-chip bandwidth (GB/s, rated SM MHz): the roofline denominators (cs_microbench)."""
+    import ctypes as C
+    gbs, mhz = C.c_double(), C.c_double()
+    rc = load().cs_microbench(device, which, C.byref(gbs), C.byref(mhz))
+    if rc != 0:
+        raise CsError(rc, "cs_microbench", _lib.status_string(rc))
+    return float(gbs.value), float(mhz.value)

@@ -126,6 +126,7 @@ SIGNATURES = {
     "cs_device_count": (C.c_int32, []),
     "cs_philox4x32_10": (None, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, _P(C.c_uint32)]),
     "cs_status_string": (C.c_char_p, [C.c_int32]),
+    "cs_microbench": (C.c_int32, [C.c_int32, C.c_uint32, _P(C.c_double), _P(C.c_double)]),
     "cs_nq_create": (C.c_int32, [_P(CsNqConfig), _P(_VP)]),
     "cs_nq_destroy": (C.c_int32, [_VP]),
     "cs_nq_last_error": (C.c_char_p, [_VP]),
@@ -171,6 +172,8 @@ SIGNATURES = {
     "cs_es_set_window": (C.c_int32, [_VP, C.c_uint64]),
     "cs_es_init_random": (C.c_int32, [_VP]),
     "cs_es_set_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "cs_es_set_chains_async": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "cs_es_commit_chains": (C.c_int32, [_VP]),
     "cs_es_get_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
     "cs_es_get_scores": (C.c_int32, [_VP, _VP, _VP]),
     "cs_es_get_status": (C.c_int32, [_VP, _VP]),

@@ -14,6 +14,7 @@
 #include "nq_packed.cuh"
 #include "ils_kernels.cuh"
 #include "philox.cuh"
+#include "microbench.cuh"
 
 using namespace csb;
 
@@ -86,8 +87,15 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // raise it to the device's opt-in maximum, so handles of different sizes never lower each other's
 // limit and concurrent creates write the same value.
 template <typename K>
+void allow_max_smem(K kernel, int optin_bytes) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kernel));  // static + dynamic must fit the opt-in limit
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            optin_bytes - (int)fa.sharedSizeBytes));
+}
+template <typename K>
 void allow_max_smem(K kernel, const cudaDeviceProp& prop) {
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    allow_max_smem(kernel, (int)prop.sharedMemPerBlockOptin);
 }
 
 }  // namespace
@@ -123,6 +131,78 @@ extern "C" const char* cs_status_string(int32_t s) {
         case CS_ERR_UNSUPPORTED: return "unsupported configuration";
         default: return "unknown status";
     }
+}
+
+// On-chip bandwidth micro-benchmarks (microbench.cuh): measured GB/s of the conflict-free
+// shared-memory stream (all SMs) and of the L2 -> SM stream; bench.py's roofline denominators.
+extern "C" int32_t cs_microbench(int32_t device, uint32_t which, double* gbs, double* sm_mhz) {
+    if (!gbs || which > CS_MICROBENCH_L2_READ) return CS_ERR_INVALID_ARG;
+    int ndev = cs_device_count();
+    if (ndev <= 0) return CS_ERR_NO_DEVICE;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return CS_ERR_NO_DEVICE;
+    if (device >= ndev) return CS_ERR_INVALID_ARG;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    unsigned int* sink = nullptr;
+    uint4* buf = nullptr;
+    int32_t rc = CS_OK;
+    try {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaMalloc(&sink, sizeof(unsigned int)));
+        const int sms = prop.multiProcessorCount;
+        double bytes = 0.0;
+        float best_ms = 1e30f;
+        if (which == CS_MICROBENCH_L2_READ) {
+            const size_t n_vec = (size_t)(32u << 20) / 16;  // 32 MB: L2-resident on B200 (126 MB), far beyond L1
+            CU(cudaMalloc(&buf, n_vec * 16));
+            CU(cudaMemsetAsync(buf, 1, n_vec * 16, st));
+            const int passes = 24;
+            for (int rep = 0; rep < 4; ++rep) {  // rep 0 also warms L2
+                CU(cudaEventRecord(e0, st));
+                mb_l2_kernel<<<sms * 4, 512, 0, st>>>(buf, n_vec, passes, sink);
+                CU(cudaEventRecord(e1, st));
+                CU(cudaStreamSynchronize(st));
+                CU(cudaGetLastError());
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep && ms < best_ms) best_ms = ms;
+            }
+            bytes = (double)n_vec * 16.0 * passes;
+        } else {
+            const int iters = 8192;
+            for (int rep = 0; rep < 4; ++rep) {
+                CU(cudaEventRecord(e0, st));
+                if (which == CS_MICROBENCH_SMEM_LDS128) mb_smem_kernel<true><<<sms * 2, 1024, 0, st>>>(iters, sink);
+                else mb_smem_kernel<false><<<sms * 2, 1024, 0, st>>>(iters, sink);
+                CU(cudaEventRecord(e1, st));
+                CU(cudaStreamSynchronize(st));
+                CU(cudaGetLastError());
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep && ms < best_ms) best_ms = ms;
+            }
+            bytes = (double)sms * 2 * 1024 * (double)iters * 8 * (which == CS_MICROBENCH_SMEM_LDS128 ? 16.0 : 4.0);
+        }
+        *gbs = bytes / (best_ms * 1e-3) / 1e9;
+        if (sm_mhz) *sm_mhz = prop.clockRate / 1e3;  // the device's rated boost clock (for the B/clk/SM reading)
+    } catch (const CudaFail& c) {
+        fprintf(stderr, "cs_microbench: CUDA error %d (%s) at cs_api.cu:%d\n", (int)c.e, cudaGetErrorString(c.e), c.line);
+        cudaGetLastError();
+        rc = CS_ERR_CUDA;
+    } catch (...) {
+        rc = CS_ERR_CUDA;
+    }
+    cudaFree(buf);
+    cudaFree(sink);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
 }
 
 // ------------------------------------------------------------------ n-queens handle

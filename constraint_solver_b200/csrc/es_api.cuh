@@ -32,6 +32,13 @@ struct cs_es_handle {
     long long* d_ids = nullptr;      // [E] sorted employee ids
     int* d_bad = nullptr;
     size_t stage_chains = 0;
+    // double-buffered input staging (cs_es_set_chains_async / cs_es_commit_chains)
+    long long* d_stage_async = nullptr;
+    size_t stage_async_elems = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_upload = nullptr;
+    uint32_t async_first = 0, async_count = 0;
+    bool async_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;
     bool ref_mode = false;          // CS_ES_FLAG_REFERENCE_PROPOSER
@@ -81,6 +88,9 @@ void es_free(cs_es_handle* h) {
     if (h->h_totals) cudaFreeHost(h->h_totals);
     if (h->h_states) cudaFreeHost(h->h_states);
     cudaFree(h->d_stage64);
+    cudaFree(h->d_stage_async);
+    if (h->ev_upload) cudaEventDestroy(h->ev_upload);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaFree(h->d_ids);
     cudaFree(h->d_bad);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -420,6 +430,56 @@ extern "C" int32_t cs_es_set_chains(cs_es_handle* h, uint32_t first, uint32_t co
         es_refresh_stats(h);
         CU(cudaStreamSynchronize(h->stream));
         h->scored = true;
+    });
+}
+
+extern "C" int32_t cs_es_set_chains_async(cs_es_handle* h, uint32_t first, uint32_t count, const int64_t* rows) {
+    return guarded(h, [&] {
+        REQUIRE(rows, "rows is NULL");
+        es_check_range(h, first, count);
+        if (h->async_pending) throw StateFail{"an upload is already pending: call cs_es_commit_chains first"};
+        const size_t need = (size_t)count * h->stride;
+        if (!h->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming));
+        }
+        if (h->stage_async_elems < need) {
+            cudaFree(h->d_stage_async);
+            h->d_stage_async = nullptr;
+            h->stage_async_elems = 0;
+            CU(cudaMalloc(&h->d_stage_async, need * sizeof(long long)));
+            h->stage_async_elems = need;
+        }
+        // copy engine only: nothing on the handle's stream touches d_stage_async before the commit
+        CU(cudaMemcpyAsync(h->d_stage_async, rows, need * sizeof(long long), cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaEventRecord(h->ev_upload, h->copy_stream));
+        h->async_first = first;
+        h->async_count = count;
+        h->async_pending = true;
+    });
+}
+
+extern "C" int32_t cs_es_commit_chains(cs_es_handle* h) {
+    return guarded(h, [&] {
+        if (!h->async_pending) throw StateFail{"no pending upload: call cs_es_set_chains_async first"};
+        const uint32_t first = h->async_first, count = h->async_count;
+        h->async_pending = false;
+        const size_t total = (size_t)count * h->stride;
+        CU(cudaStreamWaitEvent(h->stream, h->ev_upload, 0));
+        CU(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+        es_ids_to_index_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, h->stream>>>(
+            h->d_stage_async, h->d_a + (size_t)first * h->stride, total, h->d_ids, (int)h->ids.size(), h->d_bad);
+        CU(cudaGetLastError());
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        es_reset_state_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_st, (int)first, (int)count);
+        CU(cudaGetLastError());
+        if (!h->scored && !(first == 0 && count == h->cfg.n_chains)) es_rescore(h, 0, (int)h->cfg.n_chains);
+        else es_rescore(h, (int)first, (int)count);
+        es_refresh_stats(h);
+        CU(cudaStreamSynchronize(h->stream));
+        h->scored = true;
+        REQUIRE(!bad, "solution names an employee id that is not in the employee table (stored as the first employee)");
     });
 }
 

@@ -60,7 +60,7 @@ struct IlsHost {
             int dev = 0, optin = 0;
             CU(cudaGetDevice(&dev));
             CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-            CU(cudaFuncSetAttribute(ils_perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            allow_max_smem(ils_perturb_kernel, optin);
         }
         ready = true;
     }

@@ -51,6 +51,29 @@ def exchange_best(dist, local_key: torch.Tensor, rows_of, elite: torch.Tensor, r
     return score, k & 0xFFFFFFFF
 
 
+def exchange_best_device(dist, local_key: torch.Tensor, rows_all: torch.Tensor, elite: torch.Tensor,
+                         rank: int, chains_per_rank: int) -> torch.Tensor:
+    """The same exchange with NO host round trip: the reduced key is decoded
+    on the device, the owning rank selects its chain with a device-side gather, every other rank
+    contributes zeros, and one sum-all-reduce of the elite buffer delivers it everywhere.
+
+    local_key: 1-element int64; rows_all: this rank's chains as an int16 [chains, stride] view
+    (library-owned memory); elite: int16 buffer of even length >= solution length.  Everything
+    is enqueued on the current stream; returns the reduced key as a DEVICE tensor.
+    """
+    key = local_key.clone()
+    dist.all_reduce(key, op=dist.ReduceOp.MIN)
+    gid = key & 0xFFFFFFFF
+    owner = torch.div(gid, chains_per_rank, rounding_mode="floor")
+    local = gid - owner * chains_per_rank                     # always a valid local index
+    mine = (owner == rank).to(torch.int16)                    # 1 on the owning rank, else 0
+    n = min(elite.numel(), rows_all.shape[1])
+    elite.zero_()
+    elite[:n] = rows_all.index_select(0, local)[0, :n] * mine
+    dist.all_reduce(elite.view(torch.int32), op=dist.ReduceOp.SUM)  # zeros + the elite = the elite
+    return key
+
+
 class BestExchange:
     """exchange_best bound to an NQueensChains or ScheduleChains engine running on torch's
     current stream.  The packed key keeps the global chain id in its low 32 bits for both
@@ -64,9 +87,25 @@ class BestExchange:
         self.dev = dev
         self.key = device_view(eng.best_key_device_ptr(), (1,), "<i8", dev)
         self.len = getattr(eng, "n", None) or eng.n_slots  # solution length (u16 elements)
-        self.elite = torch.zeros(self.len, dtype=torch.int16, device=dev)
+        self.elite = torch.zeros((self.len + 1) & ~1, dtype=torch.int16, device=dev)  # even: reduced as int32
+        ptr0, stride = eng.chain_device_ptr(0)
+        self.rows_all = device_view(ptr0, (chains_per_rank, stride), "<i2", dev)
+        self.reduced_key = None   # device tensor after sync_device()
         self.best_score = None
         self.best_chain = None
+
+    def sync_device(self):
+        """min-allreduce + elite delivery entirely on the device (no host sync); read the result
+        later with result()."""
+        self.reduced_key = exchange_best_device(self.dist, self.key, self.rows_all, self.elite, self.rank,
+                                                self.cpr)
+        return self.reduced_key
+
+    def result(self):
+        """(score part, global chain id) of the last sync_device(); this is the only host read."""
+        k = int(self.reduced_key.item())
+        self.best_score, self.best_chain = k >> 32, k & 0xFFFFFFFF
+        return self.best_score, self.best_chain
 
     def _rows_of(self, local_chain: int) -> torch.Tensor:
         ptr, _ = self.eng.chain_device_ptr(local_chain)
@@ -74,7 +113,7 @@ class BestExchange:
 
     def sync(self, inject_into_worst: bool = False):
         self.best_score, self.best_chain = exchange_best(self.dist, self.key, self._rows_of,
-                                                         self.elite, self.rank, self.cpr)
+                                                         self.elite[: self.len], self.rank, self.cpr)
         if inject_into_worst and self.best_chain // self.cpr != self.rank and hasattr(self.eng, "set_chain_from_device"):
             worst = int(self.eng.scores().argmax())
             self.eng.set_chain_from_device(worst, self.elite.data_ptr())

@@ -134,6 +134,15 @@ class ScheduleChains:
         self._check(self._lib.cs_es_set_chains(self._h, first_chain, count, C.c_void_p(host_ptr)),
                     "cs_es_set_chains")
 
+    def set_chains_async_ptr(self, host_ptr: int, count: int, first_chain: int = 0):
+        """start the H2D copy of `count` int64 rotas at host_ptr (pinned) on the copy stream"""
+        self._check(self._lib.cs_es_set_chains_async(self._h, first_chain, count, C.c_void_p(host_ptr)),
+                    "cs_es_set_chains_async")
+
+    def commit_chains(self):
+        """wait for the pending upload, then convert / reset / score like set_chains"""
+        self._check(self._lib.cs_es_commit_chains(self._h), "cs_es_commit_chains")
+
     def get_chains(self, first_chain: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n_chains - first_chain if count is None else count
         out = np.empty((count, self.n_slots), dtype=np.int64)

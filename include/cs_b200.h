@@ -98,6 +98,17 @@ void cs_philox4x32_10(uint64_t seed, uint32_t chain, uint32_t purpose, uint64_t 
                       uint32_t out[4]);
 const char* cs_status_string(int32_t status);
 
+/* On-chip bandwidth micro-benchmarks -- the measured denominators of the roofline the benchmark
+ * reports (the chain kernels are bound by the shared-memory data pipe or the L2 -> SM path, not by
+ * HBM; SURVEY 8(d) asks for these to be measured, not computed).  No reference equivalent.
+ *   CS_MICROBENCH_SMEM_LDS32 / _LDS128: conflict-free shared-memory loads streamed by every SM;
+ *   CS_MICROBENCH_L2_READ: 16-byte loads over a 32 MB L2-resident buffer with L1 bypassed.
+ * *gbs = best of three timed launches (CUDA events); *sm_mhz (optional) = rated SM clock. */
+#define CS_MICROBENCH_SMEM_LDS32 0u
+#define CS_MICROBENCH_SMEM_LDS128 1u
+#define CS_MICROBENCH_L2_READ 2u
+int32_t cs_microbench(int32_t device, uint32_t which, double* gbs, double* sm_mhz);
+
 /* ------------------------------------------------------------------ n-queens */
 typedef struct cs_nq_handle cs_nq_handle;
 
@@ -327,6 +338,11 @@ int32_t cs_es_set_stream(cs_es_handle* h, void* cuda_stream);
 int32_t cs_es_init_random(cs_es_handle* h);
 /* rows: int64 [count][n_days + 1] employee ids */
 int32_t cs_es_set_chains(cs_es_handle* h, uint32_t first_chain, uint32_t count, const int64_t* rows);
+/* Double-buffered input staging, as cs_nq_set_chains_async / cs_nq_commit_chains: _async starts the
+ * host -> device copy on the library's copy stream and returns (rows should be pinned and stay valid
+ * until the commit); _commit waits for it, converts ids to indices, resets and scores the chains. */
+int32_t cs_es_set_chains_async(cs_es_handle* h, uint32_t first_chain, uint32_t count, const int64_t* rows);
+int32_t cs_es_commit_chains(cs_es_handle* h);
 int32_t cs_es_get_chains(cs_es_handle* h, uint32_t first_chain, uint32_t count, int64_t* rows);
 int32_t cs_es_get_scores(cs_es_handle* h, int64_t* hard, int64_t* soft);
 int32_t cs_es_get_status(cs_es_handle* h, uint32_t* status);

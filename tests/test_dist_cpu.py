@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from constraint_solver_b200.dist import exchange_best, owner_of
+from constraint_solver_b200.dist import exchange_best, exchange_best_device, owner_of
 
 
 def _free_port():
@@ -36,6 +36,14 @@ def _worker(rank, world, port, cpr, n, out):
     # every rank must now hold rank 1's chain 3
     expect = np.random.default_rng(101).integers(0, n, size=(cpr, n)).astype(np.int16)[3]
     ok = ok and np.array_equal(elite.numpy(), expect)
+    # the host-sync-free variant delivers the same key and the same elite
+    stride = n + 3
+    rows_pad = torch.zeros((cpr, stride), dtype=torch.int16)
+    rows_pad[:, :n] = torch.from_numpy(rows)
+    elite2 = torch.full(((n + 1) & ~1,), 7, dtype=torch.int16)
+    key2 = exchange_best_device(dist, key, rows_pad, elite2, rank, cpr)
+    ok = ok and int(key2.item()) == ((2 << 32) | (1 * cpr + 3))
+    ok = ok and np.array_equal(elite2.numpy()[:n], expect) and int(elite2[n:].abs().sum()) == 0
     out[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
