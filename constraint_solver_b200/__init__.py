@@ -24,6 +24,7 @@ def device_count() -> int:
     return int(load().cs_device_count())
 
 
+ES_MAX_SLOTS = _lib.CS_ES_MAX_SLOTS  # scored slots (days x shifts per day) the scheduling kernels take
 MICROBENCH_SMEM_LDS32, MICROBENCH_SMEM_LDS128, MICROBENCH_L2_READ = 0, 1, 2
 
 

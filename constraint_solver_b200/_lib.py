@@ -115,7 +115,9 @@ class CsIlsStats(C.Structure):
 
 
 CS_ES_CHANGE, CS_ES_SWAP = 0, 1
-CS_ES_MAX_DAYS = 64
+CS_ES_MAX_SLOTS = 192
+CS_ES_MAX_DAYS = CS_ES_MAX_SLOTS
+CS_ES_MAX_SHIFTS = 3
 
 _P = C.POINTER
 _VP = C.c_void_p
@@ -166,6 +168,9 @@ SIGNATURES = {
     "cs_es_ils_get_best": (C.c_int32, [_VP, C.c_uint32, _VP, _P(C.c_int64), _P(C.c_int64)]),
     "cs_es_ils_get_log": (C.c_int32, [_VP, C.c_uint32, _VP, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_es_create": (C.c_int32, [_P(CsEsConfig), _VP, _VP, _VP, C.c_uint64, _P(_VP)]),
+    "cs_es_create_ex": (C.c_int32, [_P(CsEsConfig), _VP, _VP, _VP, C.c_uint64, C.c_uint32, _VP, _P(_VP)]),
+    "cs_es_get_dims": (C.c_int32, [_VP, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_uint32)]),
+    "cs_es_score_full_ex": (C.c_int32, [_VP, C.c_uint32, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
     "cs_es_destroy": (C.c_int32, [_VP]),
     "cs_es_last_error": (C.c_char_p, [_VP]),
     "cs_es_set_stream": (C.c_int32, [_VP, _VP]),

@@ -8,18 +8,25 @@
 struct cs_es_handle {
     cs_es_config cfg{};
     int device = 0;
-    int stride = 0;   // D + 1 slots
+    int D = 0, S = 1, T = 0;  // days, shifts per day, scored slots (T = D * S)
+    int W = 1;                // 64-bit words per slot mask
+    bool multi = false;       // slot-generalised extension (S > 1 or a skill table with a gap)
+    int dp = 0;               // T rounded up to 4 (stride of the per-slot constant tables)
+    int stride = 0;           // T + 1 slots (phantom last)
     int threads = 128;
     int grid_cap = 1;
     size_t smem = 0;
-    EsConst K{};
+    EsConstT<3> K{};          // masks at the widest width; truncated to W words for the kernels
     std::vector<int64_t> ids;  // sorted employee ids (BTreeSet order)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint16_t* d_a = nullptr;
     uint16_t* d_best_a = nullptr;
-    u64* d_hol = nullptr;
-    u64* d_dayconst = nullptr;  // [3][64] PART, CONT14, CONT7, then the swap table (u16 per swap)
+    u64* d_hol = nullptr;     // [E][W] holiday slot mask per employee
+    u64* d_unsk = nullptr;    // [E][W] multi: slots whose shift kind the employee is not qualified for
+    u64* d_slotc = nullptr;   // [4][dp][W] PART, CONT14, CONT7, PARTX
+    uint16_t* d_tri = nullptr;  // [2][n_swap] (d1 << 8 | d2): enumeration order, then scan order
+    size_t n_swap = 0;
     EsChainState* d_st = nullptr;
     EsTraceEntry* d_trace = nullptr;
     unsigned int* d_work = nullptr;
@@ -49,16 +56,55 @@ struct cs_es_handle {
 
 namespace {
 
-EsParams es_params(cs_es_handle* h, int first, int count) {
-    EsParams p{};
-    p.K = h->K;
+template <int W>
+Bits<W> es_narrow(const Bits<3>& b) {
+    Bits<W> r;
+    for (int i = 0; i < W; ++i) r.w[i] = b.w[i];
+    return r;
+}
+
+template <int W>
+EsConstT<W> es_const(const cs_es_handle* h) {
+    const EsConstT<3>& k = h->K;
+    EsConstT<W> r;
+    r.D = k.D; r.S = k.S; r.T = k.T; r.E = k.E; r.start_wd = k.start_wd; r.n14 = k.n14; r.n7 = k.n7;
+    r.valid = es_narrow<W>(k.valid);
+    r.wkend = es_narrow<W>(k.wkend);
+    r.satf = es_narrow<W>(k.satf);
+    r.sd1 = es_narrow<W>(k.sd1);
+    r.sd2 = es_narrow<W>(k.sd2);
+    for (int i = 0; i < 5; ++i) r.wd[i] = es_narrow<W>(k.wd[i]);
+    return r;
+}
+
+// run f(integral_constant<int, W>, bool_constant<MULTI>) for the handle's kernel variant
+template <typename F>
+void es_dispatch(const cs_es_handle* h, F&& f) {
+    using std::integral_constant;
+    switch (h->W * 2 + (h->multi ? 1 : 0)) {
+        case 2: f(integral_constant<int, 1>{}, std::false_type{}); break;
+        case 3: f(integral_constant<int, 1>{}, std::true_type{}); break;
+        case 4: f(integral_constant<int, 2>{}, std::false_type{}); break;
+        case 5: f(integral_constant<int, 2>{}, std::true_type{}); break;
+        case 6: f(integral_constant<int, 3>{}, std::false_type{}); break;
+        default: f(integral_constant<int, 3>{}, std::true_type{}); break;
+    }
+}
+
+template <int W>
+EsParamsT<W> es_params(cs_es_handle* h, int first, int count) {
+    EsParamsT<W> p{};
+    p.K = es_const<W>(h);
     p.first_chain = first;
     p.n_chains = count;
     p.stride = h->stride;
     p.a = h->d_a;
     p.best_a = h->d_best_a;
-    p.hol = h->d_hol;
-    p.dayconst = h->d_dayconst;
+    p.hol = (const Bits<W>*)h->d_hol;
+    p.unsk = (const Bits<W>*)h->d_unsk;
+    p.slotc = (const Bits<W>*)h->d_slotc;
+    p.tri = h->d_tri;
+    p.tri_scan = h->d_tri + h->n_swap;
     p.st = h->d_st;
     p.trace = h->d_trace;
     p.trace_cap = (int)h->cfg.trace_capacity;
@@ -71,6 +117,16 @@ EsParams es_params(cs_es_handle* h, int first, int count) {
     return p;
 }
 
+// what differs between launches of the step kernel
+struct EsRun {
+    int first = 0, count = 0;
+    unsigned long long max_steps = 0, allow = 0;
+    int ls_mode = 0;
+    long long* dump_h = nullptr;
+    long long* dump_s = nullptr;
+    const unsigned int* skip = nullptr;
+};
+
 void es_free(cs_es_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -78,7 +134,9 @@ void es_free(cs_es_handle* h) {
     cudaFree(h->d_a);
     cudaFree(h->d_best_a);
     cudaFree(h->d_hol);
-    cudaFree(h->d_dayconst);
+    cudaFree(h->d_unsk);
+    cudaFree(h->d_slotc);
+    cudaFree(h->d_tri);
     cudaFree(h->d_st);
     cudaFree(h->d_trace);
     cudaFree(h->d_work);
@@ -104,16 +162,31 @@ void es_check_range(cs_es_handle* h, uint32_t first, uint32_t count) {
             "chain range outside [0, n_chains)");
 }
 
-void es_launch_step(cs_es_handle* h, int grid, const EsParams& p) {
-    if (h->ref_mode) es_step_kernel<true><<<grid, h->threads, h->smem, h->stream>>>(p);
-    else es_step_kernel<false><<<grid, h->threads, h->smem, h->stream>>>(p);
+void es_launch_step(cs_es_handle* h, int grid, const EsRun& r) {
+    es_dispatch(h, [&](auto w, auto m) {
+        constexpr int W = decltype(w)::value;
+        constexpr bool MULTI = decltype(m)::value;
+        EsParamsT<W> p = es_params<W>(h, r.first, r.count);
+        p.max_steps = r.max_steps;
+        p.allow_no_improve = r.allow;
+        p.ls_mode = r.ls_mode;
+        p.dump_h = r.dump_h;
+        p.dump_s = r.dump_s;
+        p.skip = r.skip;
+        if (!MULTI && h->ref_mode) es_step_kernel<W, false, true><<<grid, h->threads, h->smem, h->stream>>>(p);
+        else es_step_kernel<W, MULTI, false><<<grid, h->threads, h->smem, h->stream>>>(p);
+    });
     CU(cudaGetLastError());
 }
 
 void es_rescore(cs_es_handle* h, int first, int count) {
-    EsParams p = es_params(h, first, count);
     const int grid = count < h->grid_cap ? count : h->grid_cap;
-    es_rescore_kernel<<<grid, h->threads, h->smem, h->stream>>>(p);
+    es_dispatch(h, [&](auto w, auto m) {
+        constexpr int W = decltype(w)::value;
+        constexpr bool MULTI = decltype(m)::value;
+        EsParamsT<W> p = es_params<W>(h, first, count);
+        es_rescore_kernel<W, MULTI><<<grid, h->threads, h->smem, h->stream>>>(p);
+    });
     CU(cudaGetLastError());
 }
 
@@ -127,15 +200,17 @@ void es_refresh_stats(cs_es_handle* h) {
 void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
             unsigned long long allow, int ls_mode, cs_es_step_stats* stats) {
     if (!h->scored) throw StateFail{"chains have no solution yet: call cs_es_init_random or cs_es_set_chains first"};
-    EsParams p = es_params(h, first, count);
-    p.max_steps = max_steps;
-    p.allow_no_improve = allow;
-    p.ls_mode = ls_mode;
+    EsRun r;
+    r.first = first;
+    r.count = count;
+    r.max_steps = max_steps;
+    r.allow = allow;
+    r.ls_mode = ls_mode;
     CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
     CU(cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
     const int grid = count < h->grid_cap ? count : h->grid_cap;
     CU(cudaEventRecord(h->ev0, h->stream));
-    es_launch_step(h, grid, p);
+    es_launch_step(h, grid, r);
     es_refresh_stats(h);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
@@ -231,17 +306,20 @@ const EsChainState* es_states(cs_es_handle* h, uint32_t first, uint32_t count) {
     return h->h_states;
 }
 
+inline void es_set_bit(Bits<3>& b, int d) { b.w[d >> 6] |= 1ull << (d & 63); }
+
 }  // namespace
 
-extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee_ids,
-                                const int64_t* hol_emp, const int64_t* hol_day, uint64_t n_hol,
-                                cs_es_handle** out) {
+extern "C" int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* employee_ids,
+                                   const int64_t* hol_emp, const int64_t* hol_day, uint64_t n_hol,
+                                   uint32_t shifts_per_day, const uint32_t* skills, cs_es_handle** out) {
     if (!cfg || !out || !employee_ids) return CS_ERR_INVALID_ARG;
     *out = nullptr;
     if (cfg->n_days < 1 || cfg->n_employees < 1 || cfg->n_employees > 65535 || cfg->n_chains < 1 ||
-        cfg->start_weekday > 6)
+        cfg->start_weekday > 6 || shifts_per_day < 1)
         return CS_ERR_INVALID_ARG;
-    if (cfg->n_days > CS_ES_MAX_DAYS) return CS_ERR_UNSUPPORTED;
+    if (shifts_per_day > CS_ES_MAX_SHIFTS || (uint64_t)cfg->n_days * shifts_per_day > CS_ES_MAX_SLOTS)
+        return CS_ERR_UNSUPPORTED;
     if (n_hol && (!hol_emp || !hol_day)) return CS_ERR_INVALID_ARG;
     if ((uint64_t)cfg->chain_offset + cfg->n_chains > 0xffffffffull) return CS_ERR_INVALID_ARG;
     // argument validation that needs no device comes first (the reference would panic)
@@ -250,6 +328,15 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
     if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) return CS_ERR_INVALID_ARG;
     for (uint64_t k = 0; k < n_hol; ++k)
         if (hol_day[k] < 0 || hol_day[k] >= (int64_t)cfg->n_days) return CS_ERR_INVALID_ARG;
+    const int D = (int)cfg->n_days, S = (int)shifts_per_day, T = D * S, E = (int)cfg->n_employees;
+    // the extension kernels are only needed for several shifts per day or when somebody lacks a skill
+    bool skill_gap = false;
+    if (skills)
+        for (int k = 0; k < E; ++k)
+            if ((skills[k] & ((1u << S) - 1u)) != ((1u << S) - 1u)) skill_gap = true;
+    const bool multi = S > 1 || skill_gap;
+    const bool ref_mode = (cfg->flags & CS_ES_FLAG_REFERENCE_PROPOSER) != 0;
+    if (ref_mode && multi) return CS_ERR_UNSUPPORTED;  // the reference's proposer belongs to the reference's rota
     int ndev = cs_device_count();
     if (ndev <= 0) return CS_ERR_NO_DEVICE;
     int dev = cfg->device;
@@ -262,84 +349,130 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
     h->cfg = *cfg;
     h->device = dev;
     h->ids = ids;
+    h->D = D;
+    h->S = S;
+    h->T = T;
+    h->W = (T + 63) / 64;
+    h->multi = multi;
+    h->dp = (T + 3) & ~3;
     const int32_t rc = guarded(h, [&] {
-        const int D = (int)cfg->n_days, E = (int)cfg->n_employees;
-        h->stride = D + 1;
-        EsConst& K = h->K;
+        const int W = h->W, dp = h->dp;
+        h->stride = T + 1;
+        EsConstT<3>& K = h->K;
         K.D = D;
+        K.S = S;
+        K.T = T;
         K.E = E;
         K.start_wd = (int)cfg->start_weekday;
         K.n14 = D >= 14 ? D - 13 : 0;
         K.n7 = D >= 7 ? D - 6 : 0;
-        K.valid = D == 64 ? ~0ull : ((1ull << D) - 1);
-        K.wkend = 0;
-        K.satf = 0;
-        for (int w = 0; w < 7; ++w) K.wd[w] = 0;
-        for (int d = 0; d < D; ++d) {
-            const int w = (K.start_wd + d) % 7;
-            K.wd[w] |= 1ull << d;
-            if (w >= 5) K.wkend |= 1ull << d;
-            if (w == 5 && d + 9 <= D) K.satf |= 1ull << d;  // windows(9) start, lib.rs:295-302
+        K.valid = Bits<3>::lowmask(T);
+        K.wkend = K.satf = K.sd1 = K.sd2 = Bits<3>::zero();
+        for (int w = 0; w < 5; ++w) K.wd[w] = Bits<3>::zero();
+        auto slot = [&](int day, int sh) { return day * S + sh; };
+        for (int t = 0; t < T; ++t) {
+            const int day = t / S, sh = t % S;
+            const int w = (K.start_wd + day) % 7;
+            if (w < 5) es_set_bit(K.wd[w], t);
+            else es_set_bit(K.wkend, t);
+            if (w == 5 && day + 9 <= D) es_set_bit(K.satf, t);  // windows(9) start, lib.rs:295-302
+            if (sh + 1 < S) es_set_bit(K.sd1, t);
+            if (sh + 2 < S) es_set_bit(K.sd2, t);
         }
-        // per-day constants of the hot loop: H2/H3 partner days and the window starts holding d
-        std::vector<u64> dayc(3 * 64, 0ull);
-        for (int d = 0; d < D; ++d) {
-            if (d > 0) dayc[d] |= 1ull << (d - 1);          // H2, lib.rs:286-292
-            if (d + 1 < D) dayc[d] |= 1ull << (d + 1);
+        // per-slot constants of the hot loop: H2/H3 partner slots, the window starts holding the
+        // slot's day, the other slots of the same day
+        std::vector<Bits<3>> sc(4 * (size_t)dp, Bits<3>::zero());
+        for (int t = 0; t < T; ++t) {
+            const int day = t / S;
+            if (t > 0) es_set_bit(sc[t], t - 1);          // H2, lib.rs:286-292 (consecutive slots)
+            if (t + 1 < T) es_set_bit(sc[t], t + 1);
             for (int w = 0; w < K.n14; ++w)
-                if (w <= d && d <= w + 13) dayc[64 + d] |= 1ull << w;
+                if (w <= day && day <= w + 13) es_set_bit(sc[dp + t], w);
             for (int w = 0; w < K.n7; ++w)
-                if (w <= d && d <= w + 6) dayc[128 + d] |= 1ull << w;
+                if (w <= day && day <= w + 6) es_set_bit(sc[2 * dp + t], w);
+            for (int sh = 0; sh < S; ++sh)
+                if (slot(day, sh) != t) es_set_bit(sc[3 * dp + t], slot(day, sh));
         }
-        for (int sat = 0; sat < D; ++sat) {                 // H3, lib.rs:295-315
-            if (!((K.satf >> sat) & 1ull)) continue;
-            const int pr[4][2] = {{sat, sat + 7}, {sat, sat + 8}, {sat + 1, sat + 7}, {sat + 1, sat + 8}};
-            for (auto& q : pr) {
-                dayc[q[0]] |= 1ull << q[1];
-                dayc[q[1]] |= 1ull << q[0];
+        for (int sat = 0; sat + 9 <= D; ++sat) {          // H3, lib.rs:295-315, per shift
+            if ((K.start_wd + sat) % 7 != 5) continue;
+            for (int sh = 0; sh < S; ++sh) {
+                const int pr[4][2] = {{sat, sat + 7}, {sat, sat + 8}, {sat + 1, sat + 7}, {sat + 1, sat + 8}};
+                for (auto& q : pr) {
+                    es_set_bit(sc[slot(q[0], sh)], slot(q[1], sh));
+                    es_set_bit(sc[slot(q[1], sh)], slot(q[0], sh));
+                }
             }
         }
-        {   // swap r -> (d1 << 8 | d2), enumeration order d1 < d2 row-major; appended as u16
-            const size_t n_swap = (size_t)D * (D - 1) / 2;
-            const size_t words = (n_swap + 3) / 4 + 1;
-            dayc.resize(3 * 64 + 2 * words, 0ull);
-            uint16_t* tri = (uint16_t*)(dayc.data() + 192);
+        std::vector<u64> slotc(4 * (size_t)dp * W);
+        for (size_t k = 0; k < sc.size(); ++k)
+            for (int i = 0; i < W; ++i) slotc[k * W + i] = sc[k].w[i];
+        // swap r -> (d1 << 8 | d2), enumeration order d1 < d2 row-major; then the same pairs in SCAN
+        // order: pairs closer than 14 days (whose windows overlap and need the both-day corrections)
+        // first, so a warp's 32 swaps take the same path; move ids stay row-major
+        h->n_swap = (size_t)T * (T - 1) / 2;
+        std::vector<uint16_t> tri(2 * h->n_swap + 8, 0);
+        {
             size_t r = 0;
-            for (int d1 = 0; d1 < D; ++d1)
-                for (int d2 = d1 + 1; d2 < D; ++d2) tri[r++] = (uint16_t)((d1 << 8) | d2);
-            // the same pairs in SCAN order: pairs closer than 14 days (whose windows overlap and need the
-            // both-day corrections) first, so a warp's 32 swaps take the same path; move ids stay row-major
-            uint16_t* scan = (uint16_t*)(dayc.data() + 192 + words);
-            r = 0;
+            for (int d1 = 0; d1 < T; ++d1)
+                for (int d2 = d1 + 1; d2 < T; ++d2) tri[r++] = (uint16_t)((d1 << 8) | d2);
+            r = h->n_swap;
             for (int pass = 0; pass < 2; ++pass)
-                for (int d1 = 0; d1 < D; ++d1)
-                    for (int d2 = d1 + 1; d2 < D; ++d2)
-                        if ((d2 - d1 < 14) == (pass == 0)) scan[r++] = (uint16_t)((d1 << 8) | d2);
+                for (int d1 = 0; d1 < T; ++d1)
+                    for (int d2 = d1 + 1; d2 < T; ++d2)
+                        if ((d2 / S - d1 / S < 14) == (pass == 0)) tri[r++] = (uint16_t)((d1 << 8) | d2);
         }
-        std::vector<u64> hol(E, 0ull);
+        std::vector<u64> hol((size_t)E * W, 0ull), unsk;
         for (uint64_t k = 0; k < n_hol; ++k) {
             const int idx = es_index_of(h, hol_emp[k]);
-            if (idx >= 0) hol[idx] |= 1ull << hol_day[k];  // unknown employees never match a day
+            if (idx < 0) continue;  // unknown employees never match a slot
+            for (int sh = 0; sh < S; ++sh) {
+                const int t = slot((int)hol_day[k], sh);
+                hol[(size_t)idx * W + (t >> 6)] |= 1ull << (t & 63);
+            }
+        }
+        if (multi) {
+            unsk.assign((size_t)E * W, 0ull);
+            if (skills)
+                for (int k = 0; k < E; ++k) {
+                    const int idx = es_index_of(h, employee_ids[k]);
+                    for (int t = 0; t < T; ++t)
+                        if (!((skills[k] >> (t % S)) & 1u)) unsk[(size_t)idx * W + (t >> 6)] |= 1ull << (t & 63);
+                }
         }
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, dev));
-        h->smem = es_smem_bytes(D, E);
+        es_dispatch(h, [&](auto w, auto m) {
+            constexpr int W_ = decltype(w)::value;
+            constexpr bool MULTI = decltype(m)::value;
+            h->smem = es_smem_bytes<W_, MULTI>(T, E);
+        });
         REQUIRE(h->smem <= (size_t)prop.sharedMemPerBlockOptin, "employee table too large for shared memory");
-        const long long moves = (long long)D * E + (long long)D * (D - 1) / 2;
-        // per-day phases keep <= 64 threads busy between barriers, so wide CTAs mostly wait (measured: 128 beats 256
-        // by 6 % at 56 x 2000, 32 beats 64 by 10 % at 28 x 50)
-        h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : 128;
-        if (const char* t = std::getenv("CS_ES_THREADS")) {  // tuning knob: CTA size (32..256, multiple of 32)
-            const int v = std::atoi(t);
-            if (v >= 32 && v <= 256 && v % 32 == 0) h->threads = v;
+        const long long moves = (long long)T * E + (long long)T * (T - 1) / 2;
+        if (W == 1 && !multi) {
+            // per-day phases keep <= 64 threads busy between barriers, so wide CTAs mostly wait (measured: 128 beats
+            // 256 by 6 % at 56 x 2000, 32 beats 64 by 10 % at 28 x 50)
+            h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : 128;
+        } else {
+            // wider masks: the tables take most of an SM's shared memory, so few CTAs are resident -- make them wide
+            h->threads = moves <= 8192 ? 64 : h->smem > (size_t)96 * 1024 ? 512 : h->smem > (size_t)48 * 1024 ? 256 : 128;
         }
-        allow_max_smem(es_step_kernel<false>, prop);
-        allow_max_smem(es_step_kernel<true>, prop);
-        h->ref_mode = (cfg->flags & CS_ES_FLAG_REFERENCE_PROPOSER) != 0;
-        allow_max_smem(es_rescore_kernel, prop);
-        allow_max_smem(es_eval_kernel, prop);
+        const int max_threads = (W == 1 && !multi) ? 256 : 512;
+        if (const char* t = std::getenv("CS_ES_THREADS")) {  // tuning knob: CTA size (multiple of 32)
+            const int v = std::atoi(t);
+            if (v >= 32 && v <= max_threads && v % 32 == 0) h->threads = v;
+        }
+        h->ref_mode = ref_mode;
         int per_sm = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel<false>, h->threads, h->smem));
+        es_dispatch(h, [&](auto w, auto m) {
+            constexpr int W_ = decltype(w)::value;
+            constexpr bool MULTI = decltype(m)::value;
+            allow_max_smem(es_step_kernel<W_, MULTI, false>, prop);
+            if (!MULTI) allow_max_smem(es_step_kernel<W_, false, true>, prop);
+            allow_max_smem(es_rescore_kernel<W_, MULTI>, prop);
+            allow_max_smem(es_eval_kernel<W_, MULTI>, prop);
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel<W_, MULTI, false>, h->threads,
+                                                             h->smem));
+        });
         if (per_sm < 1) per_sm = 1;
         h->grid_cap = prop.multiProcessorCount * per_sm;
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -347,8 +480,10 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         const size_t nc = cfg->n_chains;
         CU(cudaMalloc(&h->d_a, nc * h->stride * sizeof(uint16_t)));
         CU(cudaMalloc(&h->d_best_a, nc * h->stride * sizeof(uint16_t)));
-        CU(cudaMalloc(&h->d_hol, (size_t)E * sizeof(u64)));
-        CU(cudaMalloc(&h->d_dayconst, dayc.size() * sizeof(u64)));
+        CU(cudaMalloc(&h->d_hol, hol.size() * sizeof(u64)));
+        if (multi) CU(cudaMalloc(&h->d_unsk, unsk.size() * sizeof(u64)));
+        CU(cudaMalloc(&h->d_slotc, slotc.size() * sizeof(u64)));
+        CU(cudaMalloc(&h->d_tri, tri.size() * sizeof(uint16_t)));
         CU(cudaMalloc(&h->d_st, nc * sizeof(EsChainState)));
         if (cfg->trace_capacity)
             CU(cudaMalloc(&h->d_trace, nc * cfg->trace_capacity * sizeof(EsTraceEntry)));
@@ -365,8 +500,10 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
         CU(cudaMemcpy(h->d_ids, h->ids.data(), (size_t)E * sizeof(long long), cudaMemcpyHostToDevice));
         CU(cudaEventCreate(&h->ev0));
         CU(cudaEventCreate(&h->ev1));
-        CU(cudaMemcpyAsync(h->d_hol, hol.data(), (size_t)E * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(h->d_dayconst, dayc.data(), dayc.size() * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpy(h->d_hol, hol.data(), hol.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        if (multi) CU(cudaMemcpy(h->d_unsk, unsk.data(), unsk.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_slotc, slotc.data(), slotc.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_tri, tri.data(), tri.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CU(cudaMemsetAsync(h->d_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));
         CU(cudaMemsetAsync(h->d_best_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));
         es_reset_state_kernel<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>(h->d_st, 0, (int)nc);
@@ -381,6 +518,12 @@ extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee
     }
     *out = h;
     return CS_OK;
+}
+
+extern "C" int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee_ids,
+                                const int64_t* hol_emp, const int64_t* hol_day, uint64_t n_hol,
+                                cs_es_handle** out) {
+    return cs_es_create_ex(cfg, employee_ids, hol_emp, hol_day, n_hol, 1u, nullptr, out);
 }
 
 extern "C" int32_t cs_es_destroy(cs_es_handle* h) {
@@ -532,28 +675,54 @@ extern "C" int32_t cs_es_get_status(cs_es_handle* h, uint32_t* status) {
     });
 }
 
+namespace {
+void es_score_full10(cs_es_handle* h, uint32_t chain, long long t[10]) {
+    es_check_range(h, chain, 1);
+    long long* d_out = nullptr;
+    CU(cudaMalloc(&d_out, 10 * sizeof(long long)));
+    try {
+        es_full_score_kernel<<<1, 32, 0, h->stream>>>(h->d_a + (size_t)chain * h->stride, h->stride, 1, h->D, h->S,
+                                                      h->K.start_wd, h->d_hol, h->d_unsk, h->W, d_out);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(t, d_out, 10 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } catch (...) {
+        cudaFree(d_out);
+        throw;
+    }
+    cudaFree(d_out);
+}
+}  // namespace
+
 extern "C" int32_t cs_es_score_full(cs_es_handle* h, uint32_t chain, int64_t* hard, int64_t* soft,
                                     int64_t terms[8]) {
     return guarded(h, [&] {
-        es_check_range(h, chain, 1);
-        long long* d_out = nullptr;
-        CU(cudaMalloc(&d_out, 8 * sizeof(long long)));
-        long long t[8];
-        try {
-            es_full_score_kernel<<<1, 32, 0, h->stream>>>(h->d_a + (size_t)chain * h->stride, h->stride, 1,
-                                                          h->K, h->d_hol, d_out);
-            CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(t, d_out, sizeof t, cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaStreamSynchronize(h->stream));
-        } catch (...) {
-            cudaFree(d_out);
-            throw;
-        }
-        cudaFree(d_out);
-        if (hard) *hard = t[0] + t[1] + t[2] + t[3];
+        long long t[10];
+        es_score_full10(h, chain, t);
+        if (hard) *hard = t[0] + t[1] + t[2] + t[3] + t[8] + t[9];
         if (soft) *soft = t[4] + t[5] + t[6] + t[7];
         if (terms)
             for (int k = 0; k < 8; ++k) terms[k] = t[k];
+    });
+}
+
+extern "C" int32_t cs_es_score_full_ex(cs_es_handle* h, uint32_t chain, int64_t* hard, int64_t* soft,
+                                       int64_t terms[10]) {
+    return guarded(h, [&] {
+        long long t[10];
+        es_score_full10(h, chain, t);
+        if (hard) *hard = t[0] + t[1] + t[2] + t[3] + t[8] + t[9];
+        if (soft) *soft = t[4] + t[5] + t[6] + t[7];
+        if (terms)
+            for (int k = 0; k < 10; ++k) terms[k] = t[k];
+    });
+}
+
+extern "C" int32_t cs_es_get_dims(cs_es_handle* h, uint32_t* n_days, uint32_t* shifts_per_day, uint32_t* n_slots) {
+    return guarded(h, [&] {
+        if (n_days) *n_days = (uint32_t)h->D;
+        if (shifts_per_day) *shifts_per_day = (uint32_t)h->S;
+        if (n_slots) *n_slots = (uint32_t)h->stride;
     });
 }
 
@@ -563,7 +732,7 @@ extern "C" int32_t cs_es_eval_moves(cs_es_handle* h, uint32_t chain, const cs_es
         es_check_range(h, chain, 1);
         if (n_moves == 0) return;
         REQUIRE(moves && dhard && dsoft, "moves/dhard/dsoft is NULL");
-        const uint32_t D = h->cfg.n_days, E = h->cfg.n_employees;
+        const uint32_t D = (uint32_t)h->T, E = h->cfg.n_employees;  // D: scored slots
         // split by kind (the kernel takes one kind per launch), keep positions
         std::vector<uint2> mv[2];
         std::vector<uint64_t> pos[2];
@@ -588,8 +757,12 @@ extern "C" int32_t cs_es_eval_moves(cs_es_handle* h, uint32_t chain, const cs_es
             std::vector<long long> o(2 * cnt);
             try {
                 CU(cudaMemcpyAsync(d_m, mv[kind].data(), cnt * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
-                EsParams p = es_params(h, 0, (int)h->cfg.n_chains);
-                es_eval_kernel<<<1, 256, h->smem, h->stream>>>(p, (int)chain, kind, d_m, cnt, d_o, d_o + cnt);
+                es_dispatch(h, [&](auto w, auto m) {
+                    constexpr int W = decltype(w)::value;
+                    constexpr bool MULTI = decltype(m)::value;
+                    EsParamsT<W> p = es_params<W>(h, 0, (int)h->cfg.n_chains);
+                    es_eval_kernel<W, MULTI><<<1, 256, h->smem, h->stream>>>(p, (int)chain, kind, d_m, cnt, d_o, d_o + cnt);
+                });
                 CU(cudaGetLastError());
                 CU(cudaMemcpyAsync(o.data(), d_o, 2 * cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
                 CU(cudaStreamSynchronize(h->stream));
@@ -617,7 +790,7 @@ extern "C" int32_t cs_es_enumerate(cs_es_handle* h, uint32_t chain, cs_es_move* 
         CU(cudaMemcpyAsync(a.data(), h->d_a + (size_t)chain * h->stride, h->stride * sizeof(uint16_t),
                            cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        const uint32_t D = h->cfg.n_days, E = h->cfg.n_employees;
+        const uint32_t D = (uint32_t)h->T, E = h->cfg.n_employees;  // D: scored slots
         uint64_t k = 0;
         for (uint32_t d = 0; d < D; ++d)
             for (uint32_t e = 0; e < E; ++e) {
@@ -641,7 +814,7 @@ extern "C" int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, i
         es_check_range(h, chain, 1);
         REQUIRE(n_out, "n_out is NULL");
         if (!h->scored) throw StateFail{"no solution loaded"};
-        const uint64_t D = h->cfg.n_days, E = h->cfg.n_employees;
+        const uint64_t D = (uint64_t)h->T, E = h->cfg.n_employees;  // D: scored slots
         const uint64_t cnt = D * E + D * (D - 1) / 2;
         *n_out = cnt;
         if (!dhard || !dsoft) return;
@@ -649,12 +822,14 @@ extern "C" int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, i
         long long* d_dump = nullptr;
         CU(cudaMalloc(&d_dump, 2 * cnt * sizeof(long long)));
         try {
-            EsParams p = es_params(h, (int)chain, 1);
-            p.max_steps = 1;
-            p.dump_h = d_dump;
-            p.dump_s = d_dump + cnt;
+            EsRun r;
+            r.first = (int)chain;
+            r.count = 1;
+            r.max_steps = 1;
+            r.dump_h = d_dump;
+            r.dump_s = d_dump + cnt;
             CU(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-            es_launch_step(h, 1, p);
+            es_launch_step(h, 1, r);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(dhard, d_dump, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaMemcpyAsync(dsoft, d_dump + cnt, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
@@ -790,9 +965,11 @@ extern "C" int32_t cs_es_ils_run(cs_es_handle* h, uint32_t rounds, uint64_t ls_m
         if (!h->ils.ready) throw StateFail{"call cs_es_ils_init first"};
         const int nc = (int)h->cfg.n_chains;
         IlsParams ip = es_ils_params(h);
-        EsParams lp = es_params(h, 0, nc);
+        EsRun lp;
+        lp.first = 0;
+        lp.count = nc;
         lp.max_steps = ls_max_iterations;
-        lp.allow_no_improve = allow;
+        lp.allow = allow;
         lp.ls_mode = 1;
         lp.skip = h->ils.d_skip;
         const int ls_grid = nc < h->grid_cap ? nc : h->grid_cap;

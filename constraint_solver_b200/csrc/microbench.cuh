@@ -26,12 +26,12 @@ __global__ void __launch_bounds__(1024, 2) mb_smem_kernel(int iters, unsigned in
     unsigned int acc = 0;
     if (WIDE) {
         const uint4* b4 = (const uint4*)buf;
-        int idx = threadIdx.x;  // 1024 threads x 16 B = 16 KB per sweep; two sweeps cover the buffer
+        int idx = threadIdx.x;  // lanes read consecutive 16-byte words: conflict-free, 4 wavefronts per instruction
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint4 v = b4[(idx + (u & 1) * 1024) & (MB_SMEM_WORDS / 4 - 1)];
+            for (int u = 0; u < 8; ++u) {  // eight DISTINCT addresses per thread and iteration
+                const uint4 v = b4[(idx + u * 160) & (MB_SMEM_WORDS / 4 - 1)];
                 acc += v.x ^ v.y ^ v.z ^ v.w;
             }
             idx = (idx + 32) & (MB_SMEM_WORDS / 4 - 1);
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(1024, 2) mb_smem_kernel(int iters, unsigned in
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += buf[(idx + u * 1024) & (MB_SMEM_WORDS - 1)];
+            for (int u = 0; u < 8; ++u) acc += buf[(idx + u * 1056) & (MB_SMEM_WORDS - 1)];
             idx = (idx + 32) & (MB_SMEM_WORDS - 1);
         }
     }

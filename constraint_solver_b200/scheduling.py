@@ -61,10 +61,16 @@ class ScheduleChains:
 
     def __init__(self, n_days: int, employees: Sequence[int], *, start_weekday: int = 0,
                  holidays=(), n_chains: int = 1, seed: int = 42, chain_offset: int = 0,
-                 trace_capacity: int = 0, device: int = -1, reference_proposer: bool = False):
+                 trace_capacity: int = 0, device: int = -1, reference_proposer: bool = False,
+                 shifts_per_day: int = 1, skills=None):
+        """shifts_per_day > 1 / skills: the slot-generalised EXTENSION (not pinned by the reference):
+        n_days * shifts_per_day scored slots (slot t = day t // S, shift t % S); skills[k] is a bit
+        mask over shift kinds for employees[k] (None = everybody qualified for everything)."""
         self._lib = L.load()
         self.n_days = int(n_days)
-        self.n_slots = self.n_days + 1
+        self.shifts_per_day = int(shifts_per_day)
+        self.n_scored = self.n_days * self.shifts_per_day       # scored slots (move indices)
+        self.n_slots = self.n_scored + 1                        # + the phantom slot
         self.employees = np.ascontiguousarray(sorted(int(e) for e in employees), dtype=np.int64)
         self.n_employees = len(self.employees)
         self.n_chains = int(n_chains)
@@ -79,7 +85,16 @@ class ScheduleChains:
                            flags=L.CS_ES_FLAG_REFERENCE_PROPOSER if reference_proposer else 0)
         ids = np.ascontiguousarray(np.asarray(list(employees), dtype=np.int64))
         h = C.c_void_p()
-        rc = self._lib.cs_es_create(C.byref(cfg), _ptr(ids), _ptr(he), _ptr(hd), len(hol), C.byref(h))
+        if self.shifts_per_day == 1 and skills is None:
+            rc = self._lib.cs_es_create(C.byref(cfg), _ptr(ids), _ptr(he), _ptr(hd), len(hol), C.byref(h))
+        else:
+            sk = None
+            if skills is not None:
+                sk = np.ascontiguousarray(np.asarray(list(skills), dtype=np.uint32))
+                if len(sk) != len(ids):
+                    raise ValueError("skills must have one entry per employee")
+            rc = self._lib.cs_es_create_ex(C.byref(cfg), _ptr(ids), _ptr(he), _ptr(hd), len(hol),
+                                           self.shifts_per_day, _ptr(sk) if sk is not None else None, C.byref(h))
         if rc != L.CS_OK:
             raise L.CsError(rc, "cs_es_create", L.status_string(rc))
         self._h = h
@@ -119,10 +134,10 @@ class ScheduleChains:
         rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int64))
         if rows.ndim == 1:
             rows = rows[None, :]
-        if rows.shape[1] == self.n_days:  # no phantom supplied: repeat the last day
+        if rows.shape[1] == self.n_scored:  # no phantom supplied: repeat the last slot
             rows = np.ascontiguousarray(np.concatenate([rows, rows[:, -1:]], axis=1))
         if rows.shape[1] != self.n_slots:
-            raise ValueError("rows must have n_days + 1 (or n_days) entries")
+            raise ValueError("rows must have n_days * shifts_per_day + 1 (or without the + 1) entries")
         return rows
 
     def set_chains(self, rows, first_chain: int = 0):
@@ -174,6 +189,14 @@ class ScheduleChains:
         terms = (C.c_int64 * 8)()
         self._check(self._lib.cs_es_score_full(self._h, chain, C.byref(hard), C.byref(soft), terms),
                     "cs_es_score_full")
+        return int(hard.value), int(soft.value), [int(x) for x in terms]
+
+    def score_full_ex(self, chain: int = 0):
+        """(hard, soft, [H1..H4, S1..S4, X1 same-day overlap, X2 skill]) by the reference-loop kernel"""
+        hard, soft = C.c_int64(), C.c_int64()
+        terms = (C.c_int64 * 10)()
+        self._check(self._lib.cs_es_score_full_ex(self._h, chain, C.byref(hard), C.byref(soft), terms),
+                    "cs_es_score_full_ex")
         return int(hard.value), int(soft.value), [int(x) for x in terms]
 
     @staticmethod

@@ -282,9 +282,11 @@ int32_t cs_nq_ils_get_log(cs_nq_handle* h, uint32_t chain, int64_t* new_key, uin
  * OrderedFloat<f64> holding integers only) as two int64. */
 typedef struct cs_es_handle cs_es_handle;
 
-#define CS_ES_MAX_DAYS 64u
-#define CS_ES_CHANGE 0u /* ChangeDay: a = day, b = index into the sorted employee table, lib.rs:466-470 */
-#define CS_ES_SWAP 1u   /* SwapDays: a < b days, lib.rs:471-478 */
+#define CS_ES_MAX_SLOTS 192u /* scored slots = n_days * shifts_per_day (three 64-bit mask words) */
+#define CS_ES_MAX_DAYS CS_ES_MAX_SLOTS /* at one shift per day (the reference's rota) */
+#define CS_ES_MAX_SHIFTS 3u
+#define CS_ES_CHANGE 0u /* ChangeDay: a = day (slot), b = index into the sorted employee table, lib.rs:466-470 */
+#define CS_ES_SWAP 1u   /* SwapDays: a < b days (slots), lib.rs:471-478 */
 /* Reference mode: the reference's own move proposer -- ScheduleRandomMoveProposer, the one get_ils
  * installs (examples/employee-scheduling/src/lib.rs:60, :440-491): an endless stream of random
  * ChangeDay (weight 1) / SwapDays (weight 4) candidates drawn from a CLONE of the LocalSearch rng
@@ -295,7 +297,7 @@ typedef struct cs_es_handle cs_es_handle;
 #define CS_ES_FLAG_REFERENCE_PROPOSER 1u
 
 typedef struct cs_es_config {
-    uint32_t n_days;         /* D = end_date - start_date + 1, 1..CS_ES_MAX_DAYS */
+    uint32_t n_days;         /* D = end_date - start_date + 1; D * shifts_per_day <= CS_ES_MAX_SLOTS */
     uint32_t n_employees;    /* E >= 1; the per-chain day-mask table (8 B per employee) lives in shared memory,
                               * so E <= ~26 000 on B200 (CS_ERR_INVALID_ARG beyond: "employee table too large") */
     uint32_t start_weekday;  /* weekday of start_date, 0 = Monday .. 6 = Sunday */
@@ -331,6 +333,21 @@ typedef struct cs_es_step_stats {
  * CS_ERR_INVALID_ARG (the reference unwrap()s a None there, lib.rs:275). */
 int32_t cs_es_create(const cs_es_config* cfg, const int64_t* employee_ids, const int64_t* hol_emp,
                      const int64_t* hol_day, uint64_t n_hol, cs_es_handle** out);
+/* EXTENSION, not pinned by the reference (which has one employee per calendar DAY and no skills;
+ * BASELINE configs[2] / [3] say "3 shifts/day", the north-star names shift-overlap and skill tallies):
+ * slots = n_days x shifts_per_day, slot t = day t / S, shift t % S.  A solution is n_days * S + 1
+ * employee ids (phantom last); move indices are SLOTS.  The reference's 8 terms apply in slot units
+ * (H2 consecutive slots; H3 per shift; H4 / S1 per 14- / 7-DAY window over slot counts; a holiday
+ * covers every slot of its day) plus two hard terms: same-day overlap (pairs of slots of one day held
+ * by one employee) and skill (skills[k]: bit s set = employee_ids[k] is qualified for shift kind s;
+ * NULL = everybody for everything).  The full-re-score definition is oracle/cs_oracle.c: esx_terms.
+ * shifts_per_day = 1 with skills = NULL IS cs_es_create (same kernels, same results).  The reference
+ * proposer flag is only available there (CS_ERR_UNSUPPORTED otherwise). */
+int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* employee_ids, const int64_t* hol_emp,
+                        const int64_t* hol_day, uint64_t n_hol, uint32_t shifts_per_day,
+                        const uint32_t* skills, cs_es_handle** out);
+/* n_days, shifts_per_day, slots per solution (n_days * shifts_per_day + 1); any pointer may be NULL */
+int32_t cs_es_get_dims(cs_es_handle* h, uint32_t* n_days, uint32_t* shifts_per_day, uint32_t* n_slots);
 int32_t cs_es_destroy(cs_es_handle* h);
 const char* cs_es_last_error(const cs_es_handle* h);
 int32_t cs_es_set_stream(cs_es_handle* h, void* cuda_stream);
@@ -351,6 +368,10 @@ int32_t cs_es_get_status(cs_es_handle* h, uint32_t* status);
  * terms (optional) = H1..H4, S1..S4. */
 int32_t cs_es_score_full(cs_es_handle* h, uint32_t chain, int64_t* hard, int64_t* soft,
                          int64_t terms[8]);
+/* the same with the two extension terms: terms (optional) = H1..H4, S1..S4, X1 same-day overlap,
+ * X2 skill; hard = H1+H2+H3+H4+X1+X2 */
+int32_t cs_es_score_full_ex(cs_es_handle* h, uint32_t chain, int64_t* hard, int64_t* soft,
+                            int64_t terms[10]);
 /* exact (dhard, dsoft) of explicit moves; identity moves report INT64_MAX in both */
 int32_t cs_es_eval_moves(cs_es_handle* h, uint32_t chain, const cs_es_move* moves, uint64_t n_moves,
                          int64_t* dhard, int64_t* dsoft);

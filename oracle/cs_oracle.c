@@ -1277,3 +1277,334 @@ int64_t orc_es_neighbourhood_deltas_mt(const int64_t* a, int64_t D, int start_we
     }
     return n_change + n_swap;
 }
+
+/* ================================================================== slot-generalised scheduling
+ * EXTENSION -- NOT PINNED BY THE REFERENCE.  BASELINE configs[2] / [3] say "3 shifts/day" and the
+ * north-star names "shift overlap" and "skill" tallies; the reference has one employee per calendar
+ * DAY and neither notion (vocabulary table).  This is the in-repo CPU
+ * full-re-score definition SURVEY section 7 asks for: slots = days x shifts_per_day, slot t =
+ * day t / S, shift t % S, and it REDUCES to orc_es_score_terms at S = 1 with every employee
+ * qualified (asserted on random rotas in tests/test_oracle_cpu.py):
+ *   H1  a slot held by an employee on holiday that day                    (lib.rs:273-280 per slot)
+ *   H2  the same employee on consecutive SLOTS, a[t] == a[t+1]            (:286-292 in slot units)
+ *   H3  consecutive weekends, same shift: for Saturday i <= D-9 and each shift s, the four
+ *       pairs {Sat, Sun} x {next Sat, next Sun} of shift s                (:295-315 per shift)
+ *   H4  per 14-DAY window, employees holding more than 3 slots in it      (:318-327)
+ *   S1  per 7-day window, employees holding more than 2 slots             (:330-339)
+ *   S2  per weekday Mon-Fri with >= 2 employees, the minimum slot count   (:194-218)
+ *   S3 / S4  max - min of total / weekend slots over employees present    (:345-365)
+ *   X1  (new, hard) same-day overlap: pairs of slots of one day held by the same employee
+ *   X2  (new, hard) skill: slots whose shift kind the employee is not qualified for
+ * out[0..3] = H1..H4, out[4..7] = S1..S4, out[8] = X1, out[9] = X2;
+ * hard = H1+H2+H3+H4+X1+X2, soft = S1+S2+S3+S4. */
+typedef struct {
+    int64_t D, S, T, E, nh;
+    int wd;
+    const int64_t *he, *hd, *emp, *skills; /* skills[k]: bit s set = employees[k] works shift s; NULL = all */
+    int64_t *sid, *ssk;                    /* employee ids sorted, their skill masks */
+} esx_prob;
+
+static void esx_prob_init(esx_prob* p, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                          const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                          const int64_t* skills) {
+    p->D = D; p->S = S; p->T = D * S; p->E = E; p->nh = n_hol; p->wd = start_weekday;
+    p->he = hol_emp; p->hd = hol_day; p->emp = employees; p->skills = skills;
+    p->sid = NULL; p->ssk = NULL;
+    if (skills) { /* (id, skill) sorted by id for the lookups of X2 */
+        p->sid = (int64_t*)malloc(sizeof(int64_t) * (size_t)(E > 0 ? E : 1));
+        p->ssk = (int64_t*)malloc(sizeof(int64_t) * (size_t)(E > 0 ? E : 1));
+        for (int64_t k = 0; k < E; ++k) { /* insertion sort: E is small in the tests, 2000 in the bench */
+            int64_t q = k;
+            while (q > 0 && p->sid[q - 1] > employees[k]) {
+                p->sid[q] = p->sid[q - 1];
+                p->ssk[q] = p->ssk[q - 1];
+                --q;
+            }
+            p->sid[q] = employees[k];
+            p->ssk[q] = skills[k];
+        }
+    }
+}
+static void esx_prob_free(esx_prob* p) {
+    free(p->sid);
+    free(p->ssk);
+}
+static int64_t esx_skill_of(const esx_prob* p, int64_t id) {
+    if (!p->skills) return -1; /* every shift */
+    int64_t lo = 0, hi = p->E;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) / 2;
+        if (p->sid[mid] < id) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < p->E && p->sid[lo] == id) ? p->ssk[lo] : 0;
+}
+
+static int esx_terms(const esx_prob* p, const int64_t* a, int64_t out[10]) {
+    const int64_t D = p->D, S = p->S, T = p->T;
+    for (int k = 0; k < 10; ++k) out[k] = 0;
+    { /* H1: a holiday covers every slot of its day; duplicate (employee, day) entries count once */
+        unsigned char seen_small[1024];
+        unsigned char* seen = T <= 1024 ? seen_small : (unsigned char*)malloc((size_t)T);
+        memset(seen, 0, (size_t)(T > 0 ? T : 0));
+        int bad = 0;
+        for (int64_t k = 0; k < p->nh && !bad; ++k) {
+            if (p->hd[k] < 0 || p->hd[k] >= D) { bad = 1; break; }
+            for (int64_t s = 0; s < S; ++s) {
+                const int64_t t = p->hd[k] * S + s;
+                if (a[t] == p->he[k] && !seen[t]) {
+                    seen[t] = 1;
+                    out[0] += 1;
+                }
+            }
+        }
+        if (seen != seen_small) free(seen);
+        if (bad) return -1;
+    }
+    for (int64_t t = 0; t + 2 <= T; ++t) out[1] += (a[t] == a[t + 1]); /* H2 */
+    for (int64_t i = 0; i + 9 <= D; ++i) {                            /* H3 */
+        if (!(es_is_weekend(p->wd, i) && es_is_weekend(p->wd, i + 1))) continue;
+        for (int64_t s = 0; s < S; ++s) {
+            const int64_t d1 = i * S + s, d2 = (i + 1) * S + s, d3 = (i + 7) * S + s, d4 = (i + 8) * S + s;
+            out[2] += (a[d1] == a[d3]) + (a[d1] == a[d4]) + (a[d2] == a[d3]) + (a[d2] == a[d4]);
+        }
+    }
+    for (int64_t i = 0; i + 14 <= D; ++i) out[3] += es_window_violations(a + i * S, 14 * S, 3); /* H4 */
+    for (int64_t i = 0; i + 7 <= D; ++i) out[4] += es_window_violations(a + i * S, 7 * S, 2);   /* S1 */
+    for (int wd = 0; wd < 5; ++wd) {                                                            /* S2 */
+        int64_t distinct = 0, minc = INT64_MAX;
+        for (int64_t t = 0; t < T; ++t) {
+            if ((p->wd + t / S) % 7 != wd) continue;
+            int first = 1;
+            for (int64_t q = 0; q < t; ++q)
+                if ((p->wd + q / S) % 7 == wd && a[q] == a[t]) { first = 0; break; }
+            if (!first) continue;
+            int64_t c = 0;
+            for (int64_t q = t; q < T; ++q)
+                if ((p->wd + q / S) % 7 == wd && a[q] == a[t]) ++c;
+            ++distinct;
+            if (c < minc) minc = c;
+        }
+        if (distinct >= 2) out[5] += minc;
+    }
+    int64_t present = 0, mind = INT64_MAX, maxd = INT64_MIN, minw = INT64_MAX, maxw = INT64_MIN; /* S3, S4 */
+    for (int64_t t = 0; t < T; ++t) {
+        int first = 1;
+        for (int64_t q = 0; q < t; ++q)
+            if (a[q] == a[t]) { first = 0; break; }
+        if (!first) continue;
+        int64_t slots = 0, wk = 0;
+        for (int64_t q = t; q < T; ++q)
+            if (a[q] == a[t]) {
+                ++slots;
+                wk += es_is_weekend(p->wd, q / S);
+            }
+        ++present;
+        if (slots < mind) mind = slots;
+        if (slots > maxd) maxd = slots;
+        if (wk < minw) minw = wk;
+        if (wk > maxw) maxw = wk;
+    }
+    if (present >= 2) {
+        out[6] = maxd - mind;
+        out[7] = maxw - minw;
+    }
+    for (int64_t d = 0; d < D; ++d) /* X1 same-day overlap */
+        for (int64_t s = 0; s < S; ++s)
+            for (int64_t s2 = s + 1; s2 < S; ++s2) out[8] += (a[d * S + s] == a[d * S + s2]);
+    if (p->skills)                  /* X2 skill */
+        for (int64_t t = 0; t < T; ++t)
+            if (!((esx_skill_of(p, a[t]) >> (t % S)) & 1)) out[9] += 1;
+    return 0;
+}
+
+static int esx_score(const esx_prob* p, const int64_t* a, int64_t* hard, int64_t* soft) {
+    int64_t t[10];
+    const int rc = esx_terms(p, a, t);
+    if (rc) return rc;
+    *hard = t[0] + t[1] + t[2] + t[3] + t[8] + t[9];
+    *soft = t[4] + t[5] + t[6] + t[7];
+    return 0;
+}
+
+int orc_esx_score_terms(const int64_t* a, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                        const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                        const int64_t* skills, int64_t out[10]) {
+    esx_prob p;
+    esx_prob_init(&p, D, S, start_weekday, hol_emp, hol_day, n_hol, employees, E, skills);
+    const int rc = esx_terms(&p, a, out);
+    esx_prob_free(&p);
+    return rc;
+}
+
+/* every candidate (clone + full re-score, OpenMP over candidates), device enumeration order incl.
+ * identities: T*E change entries (slot outer, employee index inner), then T(T-1)/2 swaps */
+int64_t orc_esx_neighbourhood_deltas_mt(const int64_t* a, int64_t D, int64_t S, int start_weekday,
+                                        const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                                        const int64_t* employees, int64_t E, const int64_t* skills, int threads,
+                                        int64_t* dhard, int64_t* dsoft) {
+    esx_prob p;
+    esx_prob_init(&p, D, S, start_weekday, hol_emp, hol_day, n_hol, employees, E, skills);
+    const int64_t T = p.T;
+    int64_t h0, s0;
+    if (esx_score(&p, a, &h0, &s0)) {
+        esx_prob_free(&p);
+        return -1;
+    }
+    const int64_t n_change = T * E, n_swap = T * (T - 1) / 2;
+#pragma omp parallel num_threads(threads)
+    {
+        int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(T > 0 ? T : 1));
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t k = 0; k < n_change + n_swap; ++k) {
+            int kind;
+            int64_t x, y;
+            if (k < n_change) {
+                kind = ORC_ES_CHANGE;
+                x = k / E;
+                y = k % E;
+            } else {
+                kind = ORC_ES_SWAP;
+                int64_t r = k - n_change;
+                x = 0;
+                while (r >= T - 1 - x) {
+                    r -= T - 1 - x;
+                    ++x;
+                }
+                y = x + 1 + r;
+            }
+            memcpy(cand, a, sizeof(int64_t) * (size_t)T);
+            if (!es_apply(cand, employees, kind, x, y)) {
+                dhard[k] = INT64_MAX;
+                dsoft[k] = INT64_MAX;
+                continue;
+            }
+            int64_t h, s;
+            esx_score(&p, cand, &h, &s);
+            dhard[k] = h - h0;
+            dsoft[k] = s - s0;
+        }
+        free(cand);
+    }
+    esx_prob_free(&p);
+    return n_change + n_swap;
+}
+
+/* LocalSearch::execute (local_search.rs:301-342) over the full change + swap neighbourhood of the
+ * slot-generalised problem; same rule as orc_es_local_search (first minimum in enumeration order) */
+int64_t orc_esx_local_search(int64_t* a, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                             const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                             const int64_t* skills, uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                             int threads, int64_t* best_hard, int64_t* best_soft, int64_t* current_out,
+                             int64_t* trace_kind, int64_t* trace_x, int64_t* trace_y, int64_t* trace_hard,
+                             int64_t* trace_soft, int64_t cap) {
+    esx_prob p;
+    esx_prob_init(&p, D, S, start_weekday, hol_emp, hol_day, n_hol, employees, E, skills);
+    const int64_t T = p.T;
+    const size_t bytes = sizeof(int64_t) * (size_t)(T > 0 ? T : 1);
+    int64_t* current = (int64_t*)malloc(bytes);
+    int64_t* best = (int64_t*)malloc(bytes);
+    const int64_t n_all = T * E + T * (T - 1) / 2;
+    int64_t* dh = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_all > 0 ? n_all : 1));
+    int64_t* ds = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_all > 0 ? n_all : 1));
+    memcpy(current, a, bytes);
+    int64_t ch, cs;
+    esx_score(&p, current, &ch, &cs);
+    memcpy(best, current, bytes);
+    int64_t bh = ch, bs = cs, steps = 0;
+    uint64_t no_improvement_for = 0;
+    for (uint64_t it = 0; it < max_iterations; ++it) {
+        if (ch == 0 && cs == 0) {
+            memcpy(best, current, bytes);
+            bh = ch;
+            bs = cs;
+            break;
+        }
+        orc_esx_neighbourhood_deltas_mt(current, D, S, start_weekday, hol_emp, hol_day, n_hol, employees, E, skills,
+                                        threads, dh, ds);
+        int64_t kbest = -1;
+        for (int64_t k = 0; k < n_all; ++k) {
+            if (dh[k] == INT64_MAX) continue;
+            if (kbest < 0 || dh[k] < dh[kbest] || (dh[k] == dh[kbest] && ds[k] < ds[kbest])) kbest = k;
+        }
+        if (kbest < 0) break;
+        int64_t kind, x, y;
+        if (kbest < T * E) {
+            kind = ORC_ES_CHANGE;
+            x = kbest / E;
+            y = kbest % E;
+        } else {
+            kind = ORC_ES_SWAP;
+            int64_t r = kbest - T * E;
+            x = 0;
+            while (r >= T - 1 - x) {
+                r -= T - 1 - x;
+                ++x;
+            }
+            y = x + 1 + r;
+        }
+        const int64_t nh = ch + dh[kbest], ns = cs + ds[kbest];
+        const int improved = nh < ch || (nh == ch && ns < cs);
+        if (!improved) {
+            no_improvement_for += 1;
+            if (no_improvement_for >= allow_no_improvement_for) break;
+        }
+        es_apply(current, employees, (int)kind, x, y);
+        ch = nh;
+        cs = ns;
+        if (improved) {
+            memcpy(best, current, bytes);
+            bh = nh;
+            bs = ns;
+            no_improvement_for = 0;
+        }
+        if (steps < cap) {
+            if (trace_kind) trace_kind[steps] = kind;
+            if (trace_x) trace_x[steps] = x;
+            if (trace_y) trace_y[steps] = y;
+            if (trace_hard) trace_hard[steps] = nh;
+            if (trace_soft) trace_soft[steps] = ns;
+        }
+        ++steps;
+    }
+    memcpy(a, best, bytes);
+    if (best_hard) *best_hard = bh;
+    if (best_soft) *best_soft = bs;
+    if (current_out) memcpy(current_out, current, bytes);
+    free(current);
+    free(best);
+    free(dh);
+    free(ds);
+    esx_prob_free(&p);
+    return steps;
+}
+
+int64_t orc_esx_baseline_sample(const int64_t* a, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                                const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                                const int64_t* skills, int kind, const int64_t* x, const int64_t* y,
+                                int64_t n_moves, int threads, int64_t* checksum) {
+    esx_prob p;
+    esx_prob_init(&p, D, S, start_weekday, hol_emp, hol_day, n_hol, employees, E, skills);
+    int64_t sum = 0, h0, s0;
+    if (esx_score(&p, a, &h0, &s0)) {
+        esx_prob_free(&p);
+        return -1;
+    }
+#pragma omp parallel num_threads(threads) reduction(+ : sum)
+    {
+        int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (size_t)(p.T > 0 ? p.T : 1));
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < n_moves; ++k) {
+            memcpy(cand, a, sizeof(int64_t) * (size_t)p.T);
+            if (es_apply(cand, employees, kind, x[k], y[k])) {
+                int64_t h, s;
+                esx_score(&p, cand, &h, &s);
+                sum += (h - h0) * 1000 + (s - s0);
+            }
+        }
+        free(cand);
+    }
+    esx_prob_free(&p);
+    if (checksum) *checksum = sum;
+    return n_moves;
+}

@@ -150,6 +150,29 @@ int64_t orc_es_neighbourhood_deltas_mt(const int64_t* a, int64_t D, int start_we
                                        const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
                                        int threads, int64_t* dhard, int64_t* dsoft);
 
+/* ---- slot-generalised scheduling: EXTENSION, NOT PINNED BY THE REFERENCE (see cs_oracle.c) ----
+ * slots = D days x S shifts/day (slot t = day t / S, shift t % S), the reference's 8 terms in slot
+ * units plus X1 same-day overlap and X2 skill (skills[k]: bit s = employees[k] works shift s; NULL =
+ * everyone qualified).  Reduces to orc_es_score_terms at S = 1, skills = NULL.
+ * out[0..3] = H1..H4, out[4..7] = S1..S4, out[8] = X1, out[9] = X2. */
+int orc_esx_score_terms(const int64_t* a, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                        const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                        const int64_t* skills, int64_t out[10]);
+int64_t orc_esx_neighbourhood_deltas_mt(const int64_t* a, int64_t D, int64_t S, int start_weekday,
+                                        const int64_t* hol_emp, const int64_t* hol_day, int64_t n_hol,
+                                        const int64_t* employees, int64_t E, const int64_t* skills, int threads,
+                                        int64_t* dhard, int64_t* dsoft);
+int64_t orc_esx_local_search(int64_t* a, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                             const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                             const int64_t* skills, uint64_t allow_no_improvement_for, uint64_t max_iterations,
+                             int threads, int64_t* best_hard, int64_t* best_soft, int64_t* current_out,
+                             int64_t* trace_kind, int64_t* trace_x, int64_t* trace_y, int64_t* trace_hard,
+                             int64_t* trace_soft, int64_t cap);
+int64_t orc_esx_baseline_sample(const int64_t* a, int64_t D, int64_t S, int start_weekday, const int64_t* hol_emp,
+                                const int64_t* hol_day, int64_t n_hol, const int64_t* employees, int64_t E,
+                                const int64_t* skills, int kind, const int64_t* x, const int64_t* y,
+                                int64_t n_moves, int threads, int64_t* checksum);
+
 /* ---- iterated local search (iterated_local_search.rs:173-202; see cs_oracle.c) ---- */
 int64_t orc_nq_ils(uint64_t seed, uint32_t chain, int64_t n, int kind, uint64_t ls_max_iterations,
                    uint64_t allow_no_improvement_for, uint64_t rounds, int best_cap,

@@ -55,6 +55,9 @@ def lib():
         _lib.orc_nq_delta_baseline.restype = I64
         _lib.orc_nq_neighbourhood_deltas_mt.restype = I64
         _lib.orc_es_neighbourhood_deltas_mt.restype = I64
+        _lib.orc_esx_neighbourhood_deltas_mt.restype = I64
+        _lib.orc_esx_local_search.restype = I64
+        _lib.orc_esx_baseline_sample.restype = I64
     return _lib
 
 
@@ -400,3 +403,71 @@ def es_ils_ref(seed, chain, D, employees, start_weekday=0, holidays=None, ls_max
     r = int(r)
     return dict(rounds=r, best=employees[best], best_hard=int(bh.value), best_soft=int(bs.value),
                 round_new_key=rn[:r], round_choice=rc[:r])
+
+
+# ---------------------------------------------------------------- slot-generalised scheduling (extension)
+def esx_score_terms(a, employees, D, S, start_weekday=0, holidays=None, skills=None):
+    """EXTENSION (not pinned by the reference): D days x S shifts; int64[10] = H1..H4, S1..S4, X1, X2."""
+    a, employees = _i64(a), _i64(employees)
+    he, hd = _hol(holidays)
+    sk = _i64(skills) if skills is not None else None
+    out = np.zeros(10, dtype=np.int64)
+    rc = lib().orc_esx_score_terms(_p(a), I64(D), I64(S), C.c_int(start_weekday), _p(he), _p(hd), I64(len(he)),
+                                   _p(employees), I64(len(employees)), _p(sk), _p(out))
+    if rc:
+        raise ValueError("holiday outside the scored range")
+    return out
+
+
+def esx_score(a, employees, D, S, start_weekday=0, holidays=None, skills=None):
+    t = esx_score_terms(a, employees, D, S, start_weekday, holidays, skills)
+    return int(t[:4].sum() + t[8] + t[9]), int(t[4:8].sum())
+
+
+def esx_neighbourhood_deltas(a, employees, D, S, start_weekday=0, holidays=None, skills=None, threads=None):
+    a, employees = _i64(a), _i64(employees)
+    he, hd = _hol(holidays)
+    sk = _i64(skills) if skills is not None else None
+    T, E = D * S, len(employees)
+    cnt = T * E + T * (T - 1) // 2
+    dh = np.zeros(max(cnt, 1), dtype=np.int64)
+    ds = np.zeros(max(cnt, 1), dtype=np.int64)
+    k = lib().orc_esx_neighbourhood_deltas_mt(_p(a), I64(D), I64(S), C.c_int(start_weekday), _p(he), _p(hd),
+                                              I64(len(he)), _p(employees), I64(E), _p(sk),
+                                              C.c_int(_threads(threads)), _p(dh), _p(ds))
+    if k < 0:
+        raise ValueError("holiday outside the scored range")
+    assert k == cnt
+    return dh[:cnt], ds[:cnt]
+
+
+def esx_local_search(a, employees, D, S, start_weekday=0, holidays=None, skills=None,
+                     allow_no_improvement_for=20, max_iterations=1000, trace_cap=0, threads=None):
+    a = _i64(a).copy()
+    employees = _i64(employees)
+    he, hd = _hol(holidays)
+    sk = _i64(skills) if skills is not None else None
+    T = D * S
+    cur = np.zeros(max(T, 1), dtype=np.int64)
+    bh, bs = I64(0), I64(0)
+    tr = [np.zeros(max(trace_cap, 1), dtype=np.int64) for _ in range(5)]
+    steps = lib().orc_esx_local_search(
+        _p(a), I64(D), I64(S), C.c_int(start_weekday), _p(he), _p(hd), I64(len(he)), _p(employees),
+        I64(len(employees)), _p(sk), U64(allow_no_improvement_for), U64(max_iterations),
+        C.c_int(_threads(threads)), C.byref(bh), C.byref(bs), _p(cur), _p(tr[0]), _p(tr[1]), _p(tr[2]),
+        _p(tr[3]), _p(tr[4]), I64(trace_cap))
+    k = min(int(steps), trace_cap)
+    return dict(best=a, best_hard=int(bh.value), best_soft=int(bs.value), current=cur[:T], steps=int(steps),
+                trace_kind=tr[0][:k], trace_x=tr[1][:k], trace_y=tr[2][:k], trace_hard=tr[3][:k],
+                trace_soft=tr[4][:k])
+
+
+def esx_baseline_sample(a, employees, x, y, kind, threads, D, S, start_weekday=0, holidays=None, skills=None):
+    a, employees, x, y = _i64(a), _i64(employees), _i64(x), _i64(y)
+    he, hd = _hol(holidays)
+    sk = _i64(skills) if skills is not None else None
+    chk = I64(0)
+    k = lib().orc_esx_baseline_sample(_p(a), I64(D), I64(S), C.c_int(start_weekday), _p(he), _p(hd), I64(len(he)),
+                                      _p(employees), I64(len(employees)), _p(sk), C.c_int(kind), _p(x), _p(y),
+                                      I64(len(x)), C.c_int(threads), C.byref(chk))
+    return int(k), int(chk.value)

@@ -108,3 +108,50 @@ def get_scored_solution(solution, employee_to_holidays):  # :261-375
     if len(wk) >= 2:
         soft += max(wk) - min(wk)
     return hard, soft
+
+
+# ---------------------------------------------------------------- the slot-generalised EXTENSION
+def get_scored_solution_slots(start_date, n_days, shifts_per_day, slot_to_employee, employee_to_holidays,
+                              employee_to_skills=None):
+    """Independent rewrite of the EXTENSION's definition (oracle/cs_oracle.c: esx_terms; not pinned
+    by the reference): the rota is a list of (date, shift, employee) triples, day-major.  Returns
+    (hard, soft, terms[10]).  employee_to_skills: {employee: set of shift kinds}; None = all."""
+    S = shifts_per_day
+    rota = [(start_date + dt.timedelta(days=t // S), t % S, slot_to_employee[t]) for t in range(n_days * S)]
+    days = [start_date + dt.timedelta(days=d) for d in range(n_days)]
+    by_day = {d: [e for (dd, _s, e) in rota if dd == d] for d in days}
+    terms = [0] * 10
+    for employee, holidays in employee_to_holidays.items():              # H1: every slot of a holiday
+        for holiday in holidays:
+            if holiday not in by_day:
+                raise ValueError("holiday outside the schedule")
+            terms[0] += sum(1 for e in by_day[holiday] if e == employee)
+    for w in windows(rota, 2):                                            # H2: consecutive slots
+        terms[1] += w[0][2] == w[1][2]
+    for w in windows(days, 9):                                            # H3: per shift kind
+        if not (is_weekend(w[0]) and is_weekend(w[1])):
+            continue
+        for s in range(S):
+            a, b, c, d = by_day[w[0]][s], by_day[w[1]][s], by_day[w[7]][s], by_day[w[8]][s]
+            terms[2] += (a == c) + (a == d) + (b == c) + (b == d)
+    for w in windows(days, 14):                                           # H4: > 3 slots in 14 days
+        terms[3] += sum(1 for c in Counter(e for d in w for e in by_day[d]).values() if c > 3)
+    for w in windows(days, 7):                                            # S1: > 2 slots in 7 days
+        terms[4] += sum(1 for c in Counter(e for d in w for e in by_day[d]).values() if c > 2)
+    per_weekday = {}
+    for d, _s, e in rota:                                                 # S2
+        if not is_weekend(d):
+            per_weekday.setdefault(d.weekday(), Counter())[e] += 1
+    for counts in per_weekday.values():
+        if len(counts) > 1:
+            terms[5] += min(counts.values())
+    totals = Counter(e for _d, _s, e in rota)                             # S3 / S4
+    weekend = {e: sum(1 for d, _s, x in rota if x == e and is_weekend(d)) for e in totals}
+    if len(totals) >= 2:
+        terms[6] = max(totals.values()) - min(totals.values())
+        terms[7] = max(weekend.values()) - min(weekend.values())
+    for d in days:                                                        # X1: same-day overlap pairs
+        terms[8] += sum(c * (c - 1) // 2 for c in Counter(by_day[d]).values())
+    if employee_to_skills is not None:                                    # X2: skill
+        terms[9] = sum(1 for _d, s, e in rota if s not in employee_to_skills.get(e, set()))
+    return sum(terms[:4]) + terms[8] + terms[9], sum(terms[4:8]), terms

@@ -172,7 +172,7 @@ def test_errors_and_edge_cases():
         cs.ScheduleChains(10, [0, 1], holidays=[(0, 10)])
     assert err.value.status == L.CS_ERR_INVALID_ARG
     with pytest.raises(cs.CsError) as err:
-        cs.ScheduleChains(65, [0, 1])
+        cs.ScheduleChains(193, [0, 1])  # beyond CS_ES_MAX_SLOTS
     assert err.value.status == L.CS_ERR_UNSUPPORTED
     with pytest.raises(cs.CsError):
         cs.ScheduleChains(10, [3, 3])  # duplicate employee ids

@@ -295,3 +295,69 @@ def test_second_scorer_reproduces_the_committed_golden_vectors(golden_dir):
             table.setdefault(emp, set()).add(start + dt.timedelta(days=day))
         sol = ScheduleSolution(start, start + dt.timedelta(days=len(case["a"]) - 1), case["a"])
         assert get_scored_solution(sol, table) == (case["hard"], case["soft"])
+
+
+# ---------------------------------------------------------------- slot-generalised extension (not pinned by the reference)
+def test_extension_reduces_to_the_reference_restatement_at_one_shift_per_day():
+    rng = np.random.default_rng(31)
+    for rep in range(400):
+        D, E, wd = int(rng.integers(1, 193)), int(rng.integers(1, 14)), int(rng.integers(0, 7))
+        ids = np.sort(rng.choice(np.arange(0, 60), size=E, replace=False))
+        a = ids[rng.integers(0, E if rep % 2 else min(E, 3), size=D)]
+        hol = [(int(ids[rng.integers(0, E)]), int(rng.integers(0, D))) for _ in range(int(rng.integers(0, 3 * E)))]
+        t8, t10 = orc.es_score_terms(a, wd, hol), orc.esx_score_terms(a, ids, D, 1, wd, hol)
+        assert t8.tolist() == t10[:8].tolist() and t10[8] == 0 and t10[9] == 0, (D, E, wd)
+        assert orc.esx_score_terms(a, ids, D, 1, wd, hol, [1] * E).tolist() == t10.tolist()   # everybody qualified
+    D, E = 20, 5
+    ids = np.arange(E) * 2
+    a = ids[rng.integers(0, E, size=D)]
+    hol = [(2, 3), (8, 19)]
+    h1, s1 = orc.es_neighbourhood_deltas(a, ids, 3, hol)
+    h2, s2 = orc.esx_neighbourhood_deltas(a, ids, D, 1, 3, hol)
+    assert np.array_equal(h1, h2) and np.array_equal(s1, s2)
+    r1 = orc.es_local_search(a, ids, 3, hol, allow_no_improvement_for=4, max_iterations=12, trace_cap=16)
+    r2 = orc.esx_local_search(a, ids, D, 1, 3, hol, None, allow_no_improvement_for=4, max_iterations=12, trace_cap=16)
+    assert r1["steps"] == r2["steps"] and (r1["best_hard"], r1["best_soft"]) == (r2["best_hard"], r2["best_soft"])
+    for k in ("best", "current", "trace_kind", "trace_x", "trace_y", "trace_hard", "trace_soft"):
+        assert np.array_equal(r1[k], r2[k]), k
+
+
+def test_extension_known_answers():
+    # 2 days x 3 shifts, employee 0 everywhere, on holiday on day 1, not qualified for shift 2
+    t = orc.esx_score_terms([0] * 6, [0, 1], 2, 3, 0, [(0, 1)], [0b011, 0b111])
+    assert t.tolist() == [3, 5, 0, 0, 0, 0, 0, 0, 6, 2]
+    # 14 days x 2 shifts from a Monday, employees alternate by shift: each holds 14 slots in the one
+    # 14-day window (> 3) and 7 per 7-day window (> 2, 8 windows x 2 employees)
+    a = [0, 1] * 14
+    t = orc.esx_score_terms(a, [0, 1], 14, 2, 0)
+    assert t[1] == 0 and t[3] == 2 and t[4] == 16 and t[8] == 0 and t[6] == 0
+    assert t[2] == 8        # Sat 5 / Sun 6 vs Sat 12 / Sun 13: the same employee per shift kind, 4 pairs x 2 shifts
+    assert t[5] == 5 * 2    # every weekday: both employees hold 2 slots => min 2
+
+
+def test_extension_oracle_against_the_independent_python_rewrite():
+    import datetime as dt
+
+    from es_second_scorer import get_scored_solution_slots
+
+    rng = np.random.default_rng(777)
+    n = 0
+    for rep in range(40):
+        for D, S, E in [(1, 2, 2), (3, 3, 2), (7, 2, 3), (9, 3, 4), (14, 3, 5), (16, 2, 9), (28, 3, 50), (40, 3, 6),
+                        (64, 3, 12), (96, 2, 5)]:
+            start = dt.date(2022, 5, 9) + dt.timedelta(days=int(rng.integers(0, 7)))
+            ids = np.sort(rng.choice(np.arange(0, 3 * E + 5), size=E, replace=False)).astype(np.int64)
+            T = D * S
+            a = ids[rng.integers(0, E if rep % 2 else min(E, 3), size=T)]
+            hol = [(int(ids[rng.integers(0, E)]), int(rng.integers(0, D))) for _ in range(int(rng.integers(0, 2 * E + 2)))]
+            skills = [int(rng.integers(0, 1 << S)) for _ in range(E)]
+            table = {}
+            for emp, day in hol:
+                table.setdefault(emp, set()).add(start + dt.timedelta(days=day))
+            sk = {int(e): {s for s in range(S) if (skills[k] >> s) & 1} for k, e in enumerate(ids)}
+            hard, soft, terms = get_scored_solution_slots(start, D, S, a.tolist(), table, sk)
+            want = orc.esx_score_terms(a, ids, D, S, start.weekday(), hol, skills)
+            assert terms == want.tolist(), (D, S, E, terms, want.tolist())
+            assert (hard, soft) == orc.esx_score(a, ids, D, S, start.weekday(), hol, skills)
+            n += 1
+    assert n == 400
