@@ -662,7 +662,8 @@ def run_es(ctx, name, launches=None):
                              "(reference formulation), OpenMP over candidates"}
             cpu_ttb = cpu_es_time_to_zero_hard(name, args.seed, 40 if E <= 100 else 2)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "scaling": "weak",
-               "steps": steps, "chain_steps_per_launch": ES_LAUNCH_STEPS, "ms_per_step": ms / steps,
+               "steps": steps, "chain_steps_per_launch": ES_LAUNCH_STEPS, "moves_scored_timed": total_moves,
+               "ms_per_step": ms / steps,
                "ms_per_launch": ms / launches, "kernel_ms_per_step": kms / steps,
                "launch_overhead": {"ms_per_step_one_step_per_launch": ms1 / ES_LAUNCH_STEPS,
                                    "ms_per_step_64_steps_per_launch": ms / steps,

@@ -10,7 +10,8 @@ from .nqueens import (CHANGE, SWAP, NQueensChains, NQueensInitialSolutionGenerat
                       NQueensMoveProposer, NQueensScore, NQueensSolution,
                       NQueensSolutionScoreCalculator, ScoredSolution, StepStats)
 from .local_search import LocalSearch
-from .scheduling import ScheduleChains, ScheduleScore, ScheduleSolutionScoreCalculator
+from .scheduling import (ScheduleChains, ScheduleMoveProposer, ScheduleScore,
+                         ScheduleSolutionScoreCalculator)
 
 
 def philox4x32_10(seed: int, chain: int, purpose: int, counter: int):

@@ -330,3 +330,13 @@ class ScheduleSolutionScoreCalculator:
         self._e.set_chains(date_to_employee)
         hard, soft, _ = self._e.score_full(0)
         return ScheduleScore(float(hard), float(soft)), np.asarray(date_to_employee)
+
+
+class ScheduleMoveProposer:
+    """lib.rs:493-559 shape (the exhaustive proposer) / :440-491 (`reference=True`: the random
+    ChangeDay / SwapDays proposer get_ils installs): carries what the device needs to build the
+    handle; the neighbourhood itself is enumerated and scored on the GPU."""
+
+    def __init__(self, n_days, employees, start_weekday=0, holidays=(), reference=False):
+        self.n_days, self.employees = int(n_days), list(employees)
+        self.start_weekday, self.holidays, self.reference = start_weekday, list(holidays), reference

@@ -5,6 +5,10 @@ use std::os::raw::{c_char, c_void};
 pub const CS_OK: i32 = 0;
 pub const CS_NQ_SWAP: u32 = 0;
 pub const CS_NQ_CHANGE: u32 = 1;
+pub const CS_NQ_FLAG_REFERENCE_PROPOSER: u32 = 4;
+pub const CS_ES_CHANGE: u32 = 0;
+pub const CS_ES_SWAP: u32 = 1;
+pub const CS_ES_FLAG_REFERENCE_PROPOSER: u32 = 1;
 
 #[repr(C)] pub struct cs_nq_handle { _p: [u8; 0] }
 #[repr(C)] pub struct cs_es_handle { _p: [u8; 0] }
@@ -29,6 +33,9 @@ pub struct cs_es_config {
     pub n_days: u32, pub n_employees: u32, pub start_weekday: u32, pub n_chains: u32,
     pub chain_offset: u32, pub trace_capacity: u32, pub seed: u64, pub device: i32, pub flags: u32,
 }
+
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct cs_es_move { pub kind: u32, pub a: u32, pub b: u32 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct cs_es_step_stats {
@@ -60,6 +67,11 @@ extern "C" {
                             n: u64, delta: *mut i64) -> i32;
     pub fn cs_nq_enumerate(h: *mut cs_nq_handle, chain: u32, moves: *mut cs_move, cap: u64,
                            n_out: *mut u64) -> i32;
+    pub fn cs_nq_neighbourhood_deltas(h: *mut cs_nq_handle, chain: u32, delta: *mut i64, cap: u64,
+                                      n_out: *mut u64) -> i32;
+    pub fn cs_nq_band_deltas(h: *mut cs_nq_handle, chain: u32, i_begin: u32, i_end: u32, delta: *mut i64,
+                             cap: u64, n_out: *mut u64) -> i32;
+    pub fn cs_nq_set_window(h: *mut cs_nq_handle, window_size: u64) -> i32;
     pub fn cs_nq_step(h: *mut cs_nq_handle, n_steps: u32, stats: *mut cs_step_stats) -> i32;
     pub fn cs_nq_local_search(h: *mut cs_nq_handle, allow: u64, max_iterations: u64,
                               stats: *mut cs_step_stats) -> i32;
@@ -75,12 +87,25 @@ extern "C" {
 
     pub fn cs_es_create(cfg: *const cs_es_config, employee_ids: *const i64, hol_emp: *const i64,
                         hol_day: *const i64, n_hol: u64, out: *mut *mut cs_es_handle) -> i32;
+    pub fn cs_es_create_ex(cfg: *const cs_es_config, employee_ids: *const i64, hol_emp: *const i64,
+                           hol_day: *const i64, n_hol: u64, shifts_per_day: u32, skills: *const u32,
+                           out: *mut *mut cs_es_handle) -> i32;
+    pub fn cs_es_get_dims(h: *mut cs_es_handle, n_days: *mut u32, shifts_per_day: *mut u32, n_slots: *mut u32) -> i32;
     pub fn cs_es_destroy(h: *mut cs_es_handle) -> i32;
     pub fn cs_es_last_error(h: *const cs_es_handle) -> *const c_char;
     pub fn cs_es_init_random(h: *mut cs_es_handle) -> i32;
     pub fn cs_es_set_chains(h: *mut cs_es_handle, first: u32, count: u32, rows: *const i64) -> i32;
     pub fn cs_es_score_full(h: *mut cs_es_handle, chain: u32, hard: *mut i64, soft: *mut i64,
                             terms: *mut i64) -> i32;
+    pub fn cs_es_score_full_ex(h: *mut cs_es_handle, chain: u32, hard: *mut i64, soft: *mut i64,
+                               terms: *mut i64) -> i32;
+    pub fn cs_es_enumerate(h: *mut cs_es_handle, chain: u32, moves: *mut cs_es_move, cap: u64,
+                           n_out: *mut u64) -> i32;
+    pub fn cs_es_eval_moves(h: *mut cs_es_handle, chain: u32, moves: *const cs_es_move, n_moves: u64,
+                            dhard: *mut i64, dsoft: *mut i64) -> i32;
+    pub fn cs_es_step(h: *mut cs_es_handle, n_steps: u32, stats: *mut cs_es_step_stats) -> i32;
+    pub fn cs_es_set_chains_async(h: *mut cs_es_handle, first: u32, count: u32, rows: *const i64) -> i32;
+    pub fn cs_es_commit_chains(h: *mut cs_es_handle) -> i32;
     pub fn cs_es_set_window(h: *mut cs_es_handle, window_size: u64) -> i32;
     pub fn cs_es_local_search_one(h: *mut cs_es_handle, start: *const i64, allow: u64,
                                   max_iterations: u64, best: *mut i64, best_hard: *mut i64,

@@ -6,6 +6,9 @@
 //! `execute(start, allow_no_improvement_for)` returns the best ScoredSolution.  The move
 //! proposer, score calculator and history live behind the handle (on the GPU).
 pub mod ffi;
+/// The reference's traits -- Solution, Score, SolutionScoreCalculator, MoveProposer,
+/// InitialSolutionGenerator -- and a LocalSearch-compatible struct, implemented over the C ABI.
+pub mod traits;
 
 /// rows[col] = row, exactly the reference's `NQueensSolution.rows` (examples/nqueens/src/lib.rs:18-21)
 pub struct B200NQueensLocalSearch {

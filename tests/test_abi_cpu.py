@@ -107,3 +107,34 @@ def test_rust_ffi_declarations_match_the_header():
     assert checked >= 5
     assert "ABI version %d" % cs.load().cs_abi_version() in open(
         os.path.join(ROOT, "integration", "rust", "local-search-b200", "src", "ffi.rs")).read()
+
+
+def test_rust_shim_implements_the_reference_trait_surface():
+    """the shim implements Solution / Score / SolutionScoreCalculator / MoveProposer /
+    InitialSolutionGenerator and offers a LocalSearch-compatible struct with the reference's
+    8-argument `new` (local_search.rs:277-299) and `execute` (:301-305).  Source-only (no rustc
+    here), so keep its SHAPE under test: the trait impls exist for both problems, `new` lists the
+    reference's arguments in the reference's order, and every extern fn it calls is declared."""
+    root = os.path.join(ROOT, "integration", "rust", "local-search-b200", "src")
+    tr = open(os.path.join(root, "traits.rs")).read()
+    ffi = re.sub(r"//.*", "", open(os.path.join(root, "ffi.rs")).read())
+    for pat in (r"impl Solution for B200NQueensSolution", r"impl Score for B200NQueensScore",
+                r"impl SolutionScoreCalculator for B200NQueensScoreCalculator",
+                r"impl<R: rand::Rng> MoveProposer for B200NQueensMoveProposer<R>",
+                r"impl<R: rand::Rng> InitialSolutionGenerator for B200NQueensInitialSolutionGenerator<R>",
+                r"impl Solution for B200ScheduleSolution", r"impl Score for B200ScheduleScore",
+                r"impl SolutionScoreCalculator for B200ScheduleScoreCalculator",
+                r"impl<R: rand::Rng> MoveProposer for B200ScheduleMoveProposer<R>",
+                r"-> Box<dyn Iterator<Item = Self::Solution>>",
+                r"fn get_scored_solution\(&self, solution: Self::_Solution\) -> ScoredSolution<Self::_Solution, Self::_Score>",
+                r"pub fn execute\(&mut self, start: _Solution, allow_no_improvement_for: u64\) -> ScoredSolution<_Solution, _Score>"):
+        assert re.search(pat, tr), pat
+    ref_new = ["move_proposer", "solution_score_calculator", "max_iterations", "window_size",
+               "best_solutions_capacity", "all_solutions_capacity", "all_solution_iteration_expiry", "rng"]
+    m = re.search(r"impl<R, _Solution, _Score, SSC, MP, DP> B200LocalSearch.*?pub fn new\((.*?)\) -> Self", tr, flags=re.S)
+    args = [a.strip().split(":")[0].strip() for a in m.group(1).split(",") if a.strip()]
+    assert args[:8] == ref_new, args
+    declared = set(re.findall(r"pub fn (cs_[a-z0-9_]+)", ffi))
+    used = set(re.findall(r"ffi::(cs_[a-z0-9_]+)\(", tr))
+    assert used and used <= declared, used - declared
+    assert "pub mod traits;" in open(os.path.join(root, "lib.rs")).read()

@@ -222,3 +222,22 @@ def test_baseline_config_sizes_run_and_replay():
             dh, ds = e.eval_moves([0] * 200, x, y, 0)
             rh, rs = orc.es_eval_moves(a, ids, x, y, orc.ES_CHANGE, 0, hol)
             assert np.array_equal(dh, rh) and np.array_equal(ds, rs)
+
+
+def test_python_local_search_mirror_runs_the_scheduling_plugin():
+    """constraint_solver_b200.LocalSearch (the host mirror of local_search.rs:253-343) accepts the
+    scheduling proposer too: execute(start, allow) == the oracle's LocalSearch::execute."""
+    rng = np.random.default_rng(12)
+    D, ids, hol = 21, np.arange(5), [(1, 2), (3, 9)]
+    start = ids[rng.integers(0, 5, size=D + 1)]
+    ls = cs.LocalSearch(cs.ScheduleMoveProposer(D, ids, 0, hol), None, max_iterations=12, window_size=100)
+    score, best = ls.execute(start, 4)
+    ref = orc.es_local_search(start[:D], ids, 0, hol, allow_no_improvement_for=4, max_iterations=12)
+    assert (score.hard_score, score.soft_score) == (ref["best_hard"], ref["best_soft"])
+    assert np.array_equal(best[:D], ref["best"])
+    # the reference's own sampled proposer + window
+    ls = cs.LocalSearch(cs.ScheduleMoveProposer(D, ids, 0, hol, reference=True), None, max_iterations=12,
+                        window_size=40)
+    score, best = ls.execute(start, 4)
+    ref = orc.es_local_search_ref(start[:D], ids, 42, 0, 0, hol, 4, 12, 40)
+    assert (score.hard_score, score.soft_score) == (ref["best_hard"], ref["best_soft"])

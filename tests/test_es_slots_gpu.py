@@ -89,12 +89,13 @@ def test_long_horizon_reference_mode_and_ils():
     ids = np.arange(E, dtype=np.int64)
     with cs.ScheduleChains(D, ids, holidays=[(0, 3)], n_chains=2, seed=5) as e:
         e.init_random()
-        e.ils_init(8, log_capacity=4)
+        e.ils_init(8, 4)
         e.ils_run(3, 4, 2)
         for k in range(2):
             ref = orc.es_ils(5, k, D, ids, 0, [(0, 3)], ls_max_iterations=4, allow_no_improvement_for=2, rounds=3,
                              best_cap=8)
-            key, choice = e.ils_log(k)
+            key, choice, total = e.ils_log(k)
+            assert total == ref["rounds"]
             assert np.array_equal(key, ref["round_new_key"]) and np.array_equal(choice, ref["round_choice"])
             rows, bh, bs = e.ils_best(k)
             assert (bh, bs) == (ref["best_hard"], ref["best_soft"]) and np.array_equal(rows, ref["best"])
