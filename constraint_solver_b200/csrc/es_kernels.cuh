@@ -499,7 +499,7 @@ __device__ void es_tally(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits<W
         es_hist16_inc(s.hist2, (int)(s.histT - s.hist2) + t);
         es_hist16_inc(s.hist2, (int)(s.histW - s.hist2) + w);
         if (t < 64 * Dm::OW) bits_atomic_or(s.occT, t);
-        atomicOr(s.occW, 1ull << w);
+        bits_atomic_or32((void*)s.occW, w);
         atomicAdd(&s.misc[ES_PRESENT], 1);
         atomicAdd(&s.misc[ES_SAME], t * (t - 1) / 2);  // slot pairs held by one employee (identity swaps)
 #pragma unroll

@@ -21,4 +21,5 @@ done
 # 4. one n = 10^6 board: the packed global scan of one full-neighbourhood step
 $NCU --set full --import-source on -k regex:nqb_scan_packed_kernel -s 1 -c 1 -f -o gpurun_out/r2_nqb_scan_n1m \
     $B --workload nq1m --steps 1 --warmup 1 --no-e2e > gpurun_out/r2_prof_nq1m.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+python scripts/r2_summarise.py
+ls -la gpurun_out/
