@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcs_b200.so")
+# CS_B200_LIB: an alternative build of the SAME library (A/B experiments with compile-time knobs)
+LIB_PATH = os.environ.get("CS_B200_LIB") or os.path.join(_HERE, "libcs_b200.so")
 
 CS_OK = 0
 CS_ERR_INVALID_ARG = -1

@@ -43,6 +43,11 @@
 namespace csb {
 
 constexpr int ES_MAX_SLOTS = 192;
+#ifndef ES_BQ_VALUE
+#define ES_BQ_VALUE 2
+#endif
+constexpr int ES_BQ = ES_BQ_VALUE;  // slots per row of pass B's absent-receiver table (2: 8-byte rows, 4: 16-byte rows)
+static_assert(ES_BQ == 2 || ES_BQ == 4, "pass B reads its table rows as uint2 or uint4");
 constexpr long long ES_KEY_INF = 0x7fffffffffffffffll;
 
 // table dimensions as a function of the mask width (value ranges for T <= 64 W slots)
@@ -140,6 +145,7 @@ struct EsSmemT {
     unsigned char* dayb;   // [3][DP] per slot, for its current employee: total, weekend, weekday count
     unsigned int* base;    // [DP] packed (0x8000 - lossH) << 16 | (0x8000 - lossS1) of the slot's employee
     unsigned int* baseW;   // [DP] absent receiver without a holiday: (dh + 64) << 18 | (ds + 512) << 8 | d
+    unsigned int* bwq;     // [DP/BQ][2^BQ][BQ] !MULTI: baseW of slots BQ*q.. plus the holiday addend of bit pattern k (pass B)
     signed char* s2t;      // [DP][CBINS] S2 delta of giving slot d to an employee with cn slots on that weekday
     typename Dm::s3_t* s3t;  // [DP][TCOLS] S3 delta ... to a present employee whose total has rank j
     signed char* s4t;      // [DP][WCOLS] S4 delta ... to a present employee whose weekend count has rank j
@@ -150,7 +156,7 @@ struct EsSmemT {
 
 struct EsLayout {
     size_t mask, a, hist, occ, occT, occW, fmask, misc, red, slot, eq, smask, shol, sunsk, semp, srk, val, dwd, sday,
-        dslot, dayb, base, baseW, s2t, s3t, s4t, s4s, ga, total;
+        dslot, dayb, base, baseW, bwq, s2t, s3t, s4t, s4s, ga, total;
     int ns, dp;
 };
 __host__ __device__ inline size_t es_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -174,6 +180,7 @@ __host__ __device__ inline EsLayout es_layout(int T, int E) {
     L.shol = o;    o += (size_t)L.ns * B;
     L.sunsk = o;   o += MULTI ? (size_t)L.ns * B : 0;
     o = es_align(o, 16);
+    L.bwq = o;     o += MULTI ? 0 : (dp / ES_BQ) * (1u << ES_BQ) * ES_BQ * 4;
     L.baseW = o;   o += dp * 4;  // read as uint4
     L.base = o;    o += dp * 4;
     L.misc = o;    o += 16 * 4;
@@ -237,6 +244,7 @@ __device__ __forceinline__ EsSmemT<W> es_carve(unsigned char* p, int T, int E) {
     s.dayb = p + L.dayb;
     s.base = (unsigned int*)(p + L.base);
     s.baseW = (unsigned int*)(p + L.baseW);
+    s.bwq = (unsigned int*)(p + L.bwq);
     s.s2t = (signed char*)(p + L.s2t);
     s.s3t = (typename Dm::s3_t*)(p + L.s3t);
     s.s4t = (signed char*)(p + L.s4t);
@@ -616,24 +624,45 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
     // phase 2: what the slot's current employee loses, the value of an absent receiver, and the
     // memo tables.  The soft deltas of a change move depend on the receiving employee only
     // through its count on the weekday (S2), its total (S3) and its weekend count (S4).
-    for (int d = tid; d < s.dp; d += nt) {
-        if (d >= T) {
-            s.baseW[d] = ES_W_PAD;
-            continue;
+    for (int d0 = 0; d0 < s.dp; d0 += nt) {  // trip count uniform per warp: the quad shuffles below need whole warps
+        const int d = d0 + tid;
+        unsigned int bw = ES_W_PAD;
+        if (d < T) {
+            const int slot = s.dslot[d];
+            const Bits<W> m = s.smask[slot];
+            const Bits<W>* q = s.eq + slot * 4;
+            int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() + (q[1] & s.cont14[d]).popc();
+            if (MULTI) lossH += (m & s.partx[d]).popc();
+            const int lossS = (q[3] & s.cont7[d]).popc();
+            s.base[d] = ((unsigned)(0x8000 - lossH) << 16) | (unsigned)(0x8000 - lossS);
+            // an absent receiver: no pairs, no window counts, zero slots anywhere
+            const int to = s.dayb[d], wo = s.dayb[s.dp + d], wd = s.dwd[d];
+            const int isw = wd >= 5 ? 1 : 0;
+            int ds = -lossS + es_s3_delta(s, to, 0) + es_s4_delta(s, to, wo, isw, 0, false);
+            if (wd < 5) ds += es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], 0);
+            bw = ((unsigned)(64 - lossH) << ES_W_DH) | ((unsigned)(512 + ds) << ES_W_DS) | (unsigned)d;
         }
-        const int slot = s.dslot[d];
-        const Bits<W> m = s.smask[slot];
-        const Bits<W>* q = s.eq + slot * 4;
-        int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() + (q[1] & s.cont14[d]).popc();
-        if (MULTI) lossH += (m & s.partx[d]).popc();
-        const int lossS = (q[3] & s.cont7[d]).popc();
-        s.base[d] = ((unsigned)(0x8000 - lossH) << 16) | (unsigned)(0x8000 - lossS);
-        // an absent receiver: no pairs, no window counts, zero slots anywhere
-        const int to = s.dayb[d], wo = s.dayb[s.dp + d], wd = s.dwd[d];
-        const int isw = wd >= 5 ? 1 : 0;
-        int ds = -lossS + es_s3_delta(s, to, 0) + es_s4_delta(s, to, wo, isw, 0, false);
-        if (wd < 5) ds += es_s2_delta(s, wd, (int)s.dayb[2 * s.dp + d], 0);
-        s.baseW[d] = ((unsigned)(64 - lossH) << ES_W_DH) | ((unsigned)(512 + ds) << ES_W_DS) | (unsigned)d;
+        if (d < s.dp) s.baseW[d] = bw;
+        if (!MULTI) {
+            // pass B's table: for the quad of slots 4q..4q+3 and every 4-bit holiday pattern k, the four
+            // absent-receiver values with the holiday addend already in (one 128-bit load per 4 candidates).
+            // The quad's four lanes are neighbours; each writes 4 of the 16 patterns.
+            constexpr unsigned int HB = 1u << ES_W_DH;
+            const int lane = tid & 31, q0 = lane & ~(ES_BQ - 1), r = lane & (ES_BQ - 1);
+            unsigned int b[ES_BQ];
+#pragma unroll
+            for (int j = 0; j < ES_BQ; ++j) b[j] = __shfl_sync(0xffffffffu, bw, q0 + j);
+            if (d < s.dp) {  // the group's lanes are neighbours; each writes 2^BQ / BQ of the patterns
+                unsigned int* row = s.bwq + (d / ES_BQ) * ((1 << ES_BQ) * ES_BQ);
+                constexpr int PER = (1 << ES_BQ) / ES_BQ;
+#pragma unroll
+                for (int kk = 0; kk < PER; ++kk) {
+                    const int k = r * PER + kk;
+#pragma unroll
+                    for (int j = 0; j < ES_BQ; ++j) row[k * ES_BQ + j] = b[j] + (((k >> j) & 1) ? HB : 0u);
+                }
+            }
+        }
     }
     // dense loops: only (slot, value in use) pairs, so every lane of a warp has work
     {
@@ -879,16 +908,31 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
             for (int i = 0; i < W; ++i) {
                 const int lim = min(T - 64 * i, 64);
                 for (int d0 = 0; d0 < lim; d0 += 4) {
-                    const uint4 b = bw4[(64 * i + d0) >> 2];
-                    const unsigned int x = (unsigned int)(h.w[i] >> d0);  // holiday bits of slots d0..d0+3
-                    unsigned int w0 = b.x + ((x << ES_W_DH) & HB), w1 = b.y + ((x << (ES_W_DH - 1)) & HB);
-                    unsigned int w2 = b.z + ((x << (ES_W_DH - 2)) & HB), w3 = b.w + ((x << (ES_W_DH - 3)) & HB);
-                    if (MULTI) {
-                        const unsigned int y = (unsigned int)(u.w[i] >> d0);
-                        w0 += (y << ES_W_DH) & HB;
-                        w1 += (y << (ES_W_DH - 1)) & HB;
-                        w2 += (y << (ES_W_DH - 2)) & HB;
-                        w3 += (y << (ES_W_DH - 3)) & HB;
+                    unsigned int w0, w1, w2, w3;
+                    if (!MULTI) {  // the group's values for this employee's holiday pattern: one table row per load
+                        const unsigned int x = (unsigned int)(h.w[i] >> d0);
+                        if (ES_BQ == 4) {
+                            const uint4 b = ((const uint4*)s.bwq)[((64 * i + d0) >> 2) * 16 + (x & 15u)];
+                            w0 = b.x;
+                            w1 = b.y;
+                            w2 = b.z;
+                            w3 = b.w;
+                        } else {
+                            const uint2* t2 = (const uint2*)s.bwq + ((64 * i + d0) >> 1) * 4;
+                            const uint2 b0 = t2[x & 3u], b1 = t2[4 + ((x >> 2) & 3u)];
+                            w0 = b0.x;
+                            w1 = b0.y;
+                            w2 = b1.x;
+                            w3 = b1.y;
+                        }
+                    } else {
+                        const uint4 b = bw4[(64 * i + d0) >> 2];
+                        const unsigned int x = (unsigned int)(h.w[i] >> d0);  // holiday bits of slots d0..d0+3
+                        const unsigned int y = (unsigned int)(u.w[i] >> d0);  // missing-skill bits
+                        w0 = b.x + ((x << ES_W_DH) & HB) + ((y << ES_W_DH) & HB);
+                        w1 = b.y + ((x << (ES_W_DH - 1)) & HB) + ((y << (ES_W_DH - 1)) & HB);
+                        w2 = b.z + ((x << (ES_W_DH - 2)) & HB) + ((y << (ES_W_DH - 2)) & HB);
+                        w3 = b.w + ((x << (ES_W_DH - 3)) & HB) + ((y << (ES_W_DH - 3)) & HB);
                     }
                     w = __vimin3_u32(w, w0, w1);
                     w = __vimin3_u32(w, w2, w3);

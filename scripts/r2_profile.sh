@@ -8,7 +8,7 @@ NCU="ncu --clock-control none"
 B="python bench.py --no-cpu-baseline"
 # 1. launch list of the default command (kernel SHARE of the step)
 $B --steps 2 --warmup 1 > gpurun_out/r2_prof_plain.log 2>&1 || exit 1
-$NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file gpurun_out/r2_launches_bench_default.csv \
+$NCU --metrics gpu__time_duration.sum -c 4000 --csv --log-file gpurun_out/r2_launches_bench_default.csv \
     $B --steps 2 --warmup 1 > gpurun_out/r2_prof_launches.log 2>&1
 # 2. dominant kernel, 296 chains = two waves of 148 CTAs (the full 4096-chain launch x ~40 replays is minutes)
 $NCU --set full --import-source on -k regex:nq_step_kernel_v2 -s 1 -c 1 -f -o gpurun_out/r2_nq_step_v2 \

@@ -27,7 +27,7 @@ def summarise(rep, out, kernel, derived):
     args = [sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, os.path.join(OUT, out),
             "--kernel", kernel, "--derived"] + [f"{k}={v}" for k, v in derived.items()]
     subprocess.run(args, check=False, stdout=subprocess.DEVNULL)
-    hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot_lines.py"), rep, "45"],
+    hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot_lines.py"), rep, "400"],
                          capture_output=True, text=True).stdout
     open(os.path.join(OUT, out.replace(".json", "_hot_lines.txt")), "w").write(hot)
 
