@@ -660,7 +660,7 @@ def run_es(ctx, name, launches=None):
             cpu = {"value": v, "unit": UNIT, "cores": ctx.threads, "kind": "port",
                    "sample": f"{per_step} change candidates/step x 2 steps of one rota, clone + full re-score each "
                              "(reference formulation), OpenMP over candidates"}
-            cpu_ttb = cpu_es_time_to_zero_hard(name, args.seed, 40 if E <= 100 else 2)
+            cpu_ttb = cpu_es_time_to_zero_hard(name, args.seed, 40 if E <= 100 else (4 if S == 1 else 2))
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "scaling": "weak",
                "steps": steps, "chain_steps_per_launch": ES_LAUNCH_STEPS, "moves_scored_timed": total_moves,
                "ms_per_step": ms / steps,
