@@ -454,7 +454,9 @@ extern "C" int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* emplo
             h->threads = moves <= 2048 ? 32 : moves <= 8192 ? 64 : 128;
         } else {
             // wider masks: the tables take most of an SM's shared memory, so few CTAs are resident -- make them wide
-            h->threads = moves <= 8192 ? 64 : h->smem > (size_t)96 * 1024 ? 512 : h->smem > (size_t)48 * 1024 ? 256 : 128;
+            // (measured: 84 slots x 50: 64 / 128 / 256 threads -> 8.4 / 9.7 / 8.6e10 moves/s; 168 x 2000: 256 / 384 / 512 ->
+            // 5.4 / 6.5 / 7.0e11)
+            h->threads = moves <= 2048 ? 64 : h->smem > (size_t)96 * 1024 ? 512 : moves <= 16384 ? 128 : 256;
         }
         const int max_threads = (W == 1 && !multi) ? 256 : 512;
         if (const char* t = std::getenv("CS_ES_THREADS")) {  // tuning knob: CTA size (multiple of 32)

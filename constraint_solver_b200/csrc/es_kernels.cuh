@@ -132,7 +132,7 @@ struct EsSmemT {
     Bits<W>* cont7;     // [DP]
     Bits<W>* wdm;       // [DP] slots on the same weekday as d (0 for weekend slots)
     Bits<W>* partx;     // [DP] MULTI: the other slots of d's day
-    Bits<W>* eq;        // [NS][4] per owner: EQ3_14, EQ4_14, EQ2_7, EQ3_7 ("count == k" window starts)
+    Bits<W>* eq;        // [4][NS] per owner: EQ3_14, EQ4_14, EQ2_7, EQ3_7 ("count == k" window starts), plane-major
     Bits<W>* smask;     // [NS] slot mask of the owner's employee
     Bits<W>* shol;      // [NS] its holiday mask
     Bits<W>* sunsk;     // [NS] MULTI: its unskilled-slot mask
@@ -251,6 +251,19 @@ __device__ __forceinline__ EsSmemT<W> es_carve(unsigned char* p, int T, int E) {
     s.s4s = (signed char*)(p + L.s4s);
     s.ga = (uint16_t*)(p + L.ga);
     return s;
+}
+
+// the four "count == k" window-start masks of one owner; stored plane-major ([4][NS]) so the lanes of
+// pass A (consecutive owners) read consecutive words instead of striding by 32 bytes
+template <int W>
+struct EsEq {
+    Bits<W>* base;
+    int ns;
+    __device__ __forceinline__ Bits<W>& operator[](int k) const { return base[k * ns]; }
+};
+template <int W>
+__device__ __forceinline__ EsEq<W> es_eq(const EsSmemT<W>& s, int slot) {
+    return EsEq<W>{s.eq + slot, s.ns};
 }
 
 enum { ES_PRESENT = 0, ES_DISTINCT0 = 1, ES_HARD = 6, ES_SOFT = 7, ES_BCAST = 8, ES_NSLOT = 10, ES_SAME = 11 };
@@ -593,7 +606,7 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
             s.srk[2 * slot] = (unsigned char)occT.rank_below(t);
             s.srk[2 * slot + 1] = (unsigned char)__popcll(occW & ((1ull << w) - 1ull));
             const EsWin<W> win = es_windows<W, MULTI>(s, K, m);
-            Bits<W>* q = s.eq + slot * 4;
+            const EsEq<W> q = es_eq(s, slot);
             q[0] = win.eq3_14;
             q[1] = win.eq4_14;
             q[2] = win.eq2_7;
@@ -630,7 +643,7 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
         if (d < T) {
             const int slot = s.dslot[d];
             const Bits<W> m = s.smask[slot];
-            const Bits<W>* q = s.eq + slot * 4;
+            const EsEq<W> q = es_eq(s, slot);
             int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() + (q[1] & s.cont14[d]).popc();
             if (MULTI) lossH += (m & s.partx[d]).popc();
             const int lossS = (q[3] & s.cont7[d]).popc();
@@ -720,7 +733,7 @@ template <int W, bool MULTI>
 __device__ __forceinline__ unsigned int es_change_present_v(const EsSmemT<W>& s, int d, int slot, unsigned int& ga) {
     typedef EsDim<W> Dm;
     const Bits<W> m = s.smask[slot];
-    const Bits<W>* q = s.eq + slot * 4;
+    const EsEq<W> q = es_eq(s, slot);
     int gh = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() + (q[0] & s.cont14[d]).popc();
     if (MULTI) gh += (m & s.partx[d]).popc();
     const int gs = (q[2] & s.cont7[d]).popc();
@@ -753,8 +766,7 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmemT<W>& s, const EsC
     const int s1 = s.dslot[d1], s2 = s.dslot[d2];
     const Bits<W> nb1 = ~Bits<W>::bit(d1), nb2 = ~Bits<W>::bit(d2);
     const Bits<W> m1 = s.smask[s1], m2 = s.smask[s2];
-    const Bits<W>* q1 = s.eq + s1 * 4;
-    const Bits<W>* q2 = s.eq + s2 * 4;
+    const EsEq<W> q1 = es_eq(s, s1), q2 = es_eq(s, s2);
     // windows holding exactly one of the two slots' days change count by one for each employee
     const Bits<W> c14a = s.cont14[d1], c14b = s.cont14[d2], c7a = s.cont7[d1], c7b = s.cont7[d2];
     const Bits<W> only14a = c14a & ~c14b, only14b = c14b & ~c14a, only7a = c7a & ~c7b, only7b = c7b & ~c7a;
@@ -802,8 +814,7 @@ __device__ __forceinline__ unsigned int es_swap_from_table(const EsSmemT<W>& s, 
     if (gap < 14) {
         if (s.part[d1].test(d2)) dh -= 2;
         if (MULTI && s.partx[d1].test(d2)) dh -= 2;
-        const Bits<W>* q1 = s.eq + s1 * 4;
-        const Bits<W>* q2 = s.eq + s2 * 4;
+        const EsEq<W> q1 = es_eq(s, s1), q2 = es_eq(s, s2);
         const Bits<W> both14 = s.cont14[d1] & s.cont14[d2];
         if (both14.any())
             dh += (q1[1] & both14).popc() - (q1[0] & both14).popc() + (q2[1] & both14).popc() - (q2[0] & both14).popc();
