@@ -146,6 +146,8 @@ extern "C" int32_t cs_microbench(int32_t device, uint32_t which, double* gbs, do
     unsigned int* sink = nullptr;
     uint4* buf = nullptr;
     int32_t rc = CS_OK;
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);  // restored below: the caller's current device is not ours to change
     try {
         CU(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -202,6 +204,7 @@ extern "C" int32_t cs_microbench(int32_t device, uint32_t which, double* gbs, do
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
+    if (prev_device >= 0) cudaSetDevice(prev_device);
     return rc;
 }
 

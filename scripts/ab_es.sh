@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python -m pytest tests/test_es_gpu.py tests/test_fuzz_gpu.py tests/test_es_reference_mode_gpu.py tests/test_es_slots_gpu.py tests/test_ils_gpu.py -q -x -k "not nqueens and not nq_" > gpurun_out/ab_es_tests.log 2>&1
 tail -2 gpurun_out/ab_es_tests.log
-run() {  # workload, env assignment
+run() {  # workload, env assignment, launches
   for rep in 1 2; do
     env $2 python bench.py --workload $1 --steps ${3:-8} --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
 import sys,json
@@ -12,5 +12,5 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', '$2', '%.4g
 }
 run es2000 X=1
 run es50 X=1
-for t in 64 128 256; do run es50x3 CS_ES_THREADS=$t 4; done
-for t in 256 384 512; do run es2000x3 CS_ES_THREADS=$t 2; done
+run es50x3 X=1 4
+run es2000x3 X=1 2

@@ -224,3 +224,41 @@ def test_extension_limits_and_errors():
         st = e.step(2)
         assert st.steps_accepted == 0 and e.status()[0] == L.CHAIN_EMPTY
         assert e.score_full_ex(0)[2] == orc.esx_score_terms([7] * 6, [7], 3, 2).tolist()
+
+
+def test_random_slot_instances_every_delta_and_trajectory():
+    """Randomised sweep over the whole template space (1-3 mask words, with / without the shift and
+    skill extension): every candidate and a LocalSearch::execute trajectory against the oracle."""
+    rng = np.random.default_rng(20261019)
+    for case in range(36):
+        S = int(rng.integers(1, 4))
+        D = int(rng.integers(1, 192 // S + 1))
+        T = D * S
+        E = int(rng.integers(1, 40)) if case % 4 else int(rng.integers(1, 5))
+        wd = int(rng.integers(0, 7))
+        ids = np.sort(rng.choice(np.arange(0, 4 * E + 5), size=E, replace=False)).astype(np.int64)
+        skills = None
+        if case % 3 != 0:
+            skills = np.array([int(rng.integers(0, 1 << S)) if rng.random() < 0.5 else (1 << S) - 1 for _ in range(E)])
+        hol = [(int(ids[rng.integers(0, E)]), int(rng.integers(0, D))) for _ in range(int(rng.integers(0, 2 * E + 1)))]
+        if case % 2:
+            p = rng.dirichlet(np.full(E, 0.3))
+            start = ids[rng.choice(E, size=T + 1, p=p)]
+        else:
+            start = ids[rng.integers(0, E, size=T + 1)]
+        with cs.ScheduleChains(D, ids, start_weekday=wd, holidays=hol, n_chains=2, trace_capacity=8,
+                               shifts_per_day=S, skills=skills) as e:
+            e.set_chains(np.stack([start, start]))
+            hard, soft = e.scores()
+            assert orc.esx_score(start[:T], ids, D, S, wd, hol, skills) == (int(hard[0]), int(soft[0])), (case, D, S, E)
+            assert e.score_full_ex(0)[2] == orc.esx_score_terms(start[:T], ids, D, S, wd, hol, skills).tolist()
+            _check(e.neighbourhood_deltas(1), orc.esx_neighbourhood_deltas(start[:T], ids, D, S, wd, hol, skills),
+                   (case, D, S, E, wd))
+            ref = orc.esx_local_search(start[:T], ids, D, S, wd, hol, skills, allow_no_improvement_for=3,
+                                       max_iterations=4, trace_cap=8)
+            e.local_search(3, 4)
+            mv, th, ts, total = e.trace(0)
+            assert total == ref["steps"], (case, D, S, E)
+            assert np.array_equal(mv["kind"], ref["trace_kind"]) and np.array_equal(mv["a"], ref["trace_x"])
+            assert np.array_equal(mv["b"], ref["trace_y"])
+            assert np.array_equal(th, ref["trace_hard"]) and np.array_equal(ts, ref["trace_soft"])
