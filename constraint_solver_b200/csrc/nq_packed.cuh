@@ -30,6 +30,10 @@ namespace csb {
 #ifndef NQC_TI_VALUE
 #define NQC_TI_VALUE 16
 #endif
+#ifndef NQC_UNROLL
+#define NQC_UNROLL 2  // chunks per loop trip of the unmasked sweep (the second copy addresses with immediates)
+#endif
+constexpr int NQC_UNROLL_C = NQC_UNROLL;
 constexpr int NQC_TI = NQC_TI_VALUE;  // column slots per warp tile (TI/4 four-byte windows)
 constexpr int NQC_TJ = 4;          // columns per lane
 constexpr int NQC_CHUNK = 32 * NQC_TJ;
@@ -280,7 +284,7 @@ __device__ __forceinline__ void nqc_scan_swap(const NqSmemC& s, int n, int& best
         chunk(0, true);  // the chunk holding the tile: needs the j > i mask
         const int dj_full = (n & ~(NQC_CHUNK - 1)) - jbase;  // end of the full chunks
         int dj = NQC_CHUNK;
-#pragma unroll 2
+#pragma unroll NQC_UNROLL_C
         for (; dj < dj_full; dj += NQC_CHUNK) chunk(dj, false);
         if (jbase + dj < n) chunk(dj, true);
 
