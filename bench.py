@@ -444,7 +444,7 @@ def run_headline(ctx):
         st = one_step()
         moves += st.moves_scored
         kernel_ms += st.device_ms
-        launches += st.kernel_launches + (3 if xchg is not None else 0)
+        launches += st.kernel_launches
     ev1.record(ctx.stream)
     ctx.barrier()
     clocks = sampler.stop() if ctx.rank == 0 else None
@@ -559,7 +559,7 @@ def run_es(ctx, name, launches=None):
         st = launch()
         moves += st.moves_scored
         kms += st.device_ms
-        nl += st.kernel_launches + (3 if xchg is not None else 0)
+        nl += st.kernel_launches
     ev1.record(ctx.stream)
     ctx.barrier()
     ms = ev0.elapsed_time(ev1)
