@@ -241,3 +241,54 @@ def test_python_local_search_mirror_runs_the_scheduling_plugin():
     score, best = ls.execute(start, 4)
     ref = orc.es_local_search_ref(start[:D], ids, 42, 0, 0, hol, 4, 12, 40)
     assert (score.hard_score, score.soft_score) == (ref["best_hard"], ref["best_soft"])
+
+
+def test_async_staging_equals_synchronous_set_chains():
+    """cs_es_set_chains_async + cs_es_commit_chains (double-buffered H2D on the copy stream) leave
+    the handle exactly where cs_es_set_chains does; misuse is a state error, a bad id an argument error."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    D, ids, hol, C_ = 28, np.arange(50) * 3, [(0, 1), (9, 5), (147, 27)], 16
+    rows = ids[rng.integers(0, 50, size=(C_, D + 1))]
+    host = torch.from_numpy(np.ascontiguousarray(rows)).pin_memory()
+    with cs.ScheduleChains(D, ids, holidays=hol, n_chains=C_, trace_capacity=4) as a, \
+            cs.ScheduleChains(D, ids, holidays=hol, n_chains=C_, trace_capacity=4) as b:
+        a.set_chains(rows)
+        with pytest.raises(cs.CsError) as err:
+            b.commit_chains()                       # nothing pending
+        assert err.value.status == L.CS_ERR_STATE
+        b.set_chains_async_ptr(host.data_ptr(), C_)
+        with pytest.raises(cs.CsError) as err:
+            b.set_chains_async_ptr(host.data_ptr(), C_)   # one upload at a time
+        assert err.value.status == L.CS_ERR_STATE
+        b.commit_chains()
+        assert np.array_equal(a.get_chains(), b.get_chains())
+        ha, sa = a.scores()
+        hb, sb = b.scores()
+        assert np.array_equal(ha, hb) and np.array_equal(sa, sb)
+        a.step(3)
+        b.step(3)
+        assert np.array_equal(a.get_chains(), b.get_chains())
+        bad = host.clone().pin_memory()
+        bad[2, 5] = 1                                # not an employee id (ids are multiples of 3)
+        b.set_chains_async_ptr(bad.data_ptr(), C_)
+        with pytest.raises(cs.CsError) as err:
+            b.commit_chains()
+        assert err.value.status == L.CS_ERR_INVALID_ARG
+        b.step(1)                                    # the handle stays usable
+
+
+def test_measured_on_chip_peaks_are_plausible():
+    """cs_microbench (the roofline denominators): conflict-free shared-memory streams land within
+    60-101 % of 128 B/clk/SM x SMs x rated clock, the L2 stream beats HBM."""
+    import torch
+
+    lds32, mhz = cs.microbench(cs.MICROBENCH_SMEM_LDS32)
+    lds128, _ = cs.microbench(cs.MICROBENCH_SMEM_LDS128)
+    l2, _ = cs.microbench(cs.MICROBENCH_L2_READ)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    theory = 128.0 * sms * mhz * 1e6 / 1e9
+    assert 0.6 * theory < lds32 <= 1.01 * theory, (lds32, theory)
+    assert 0.6 * theory < lds128 <= 1.01 * theory, (lds128, theory)
+    assert l2 > 3000.0, l2
