@@ -123,21 +123,6 @@ struct Bits {
     }
     // number of set bits strictly below position f
     __device__ __forceinline__ int rank_below(int f) const { return (*this & lowmask(f)).popc(); }
-    // position of the r-th set bit (r = 0: the lowest); -1 when there are fewer
-    __device__ __forceinline__ int nth(int r) const {
-        Bits x = *this;
-#pragma unroll 1
-        for (int k = 0; k < r; ++k) {
-            bool done = false;
-#pragma unroll
-            for (int i = 0; i < W; ++i)
-                if (!done && x.w[i]) {
-                    x.w[i] &= x.w[i] - 1ull;
-                    done = true;
-                }
-        }
-        return x.ffs();
-    }
 };
 
 // set bit d of a bitset in shared memory: a NATIVE 32-bit atomic on the half-word that holds it (a 64-bit

@@ -614,22 +614,21 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
         }
     }
     // rank -> value lists of the total / weekend counts in use (j-th set bit), and per weekday the
-    // counts in use (0 first): the memo tables below are built for exactly these values
-    for (int q = nt - 1 - tid; q < Dm::VAL_BYTES; q += nt) {  // the last threads first: the first ones hold first slots
-        if (q < Dm::TCOLS) {
-            const int v = occT.nth(q);
-            s.val[q] = (unsigned char)(v >= 0 ? v : 0xff);
-        } else if (q < Dm::TCOLS + Dm::WCOLS) {
-            u64 bits = occW;
-            for (int k = 0; k < q - Dm::TCOLS; ++k) bits &= bits - 1;
-            s.val[q] = (unsigned char)(bits ? __ffsll((long long)bits) - 1 : 0xff);
-        } else if (q < Dm::VAL_C2 + 5 * Dm::CBINS) {
-            const int wd = (q - Dm::VAL_C2) / Dm::CBINS, r = (q - Dm::VAL_C2) - wd * Dm::CBINS;
-            unsigned int bits = (s.occ2[wd] & Dm::CMASK) | 1u;  // counts >= 1 in use, and 0 (a newcomer to the weekday)
-            for (int k = 0; k < r; ++k) bits &= bits - 1;
-            s.val[q] = (unsigned char)(bits ? __ffs((int)bits) - 1 : 0xff);
-        } else if (q < Dm::VAL_N2 + 5) {
-            s.val[q] = (unsigned char)__popc((s.occ2[q - Dm::VAL_N2] & Dm::CMASK) | 1u);
+    // counts in use (0 first): the memo tables below are built for exactly these values.  One thread
+    // per candidate VALUE: a value in use lands at its rank (the number of smaller values in use).
+    for (int q = nt - 1 - tid; q < Dm::TBINS + Dm::WBINS + 5 * Dm::CBINS + 5; q += nt) {  // the last threads first
+        if (q < Dm::TBINS) {
+            if (q < 64 * Dm::OW && occT.test(q)) s.val[occT.rank_below(q)] = (unsigned char)q;
+        } else if (q < Dm::TBINS + Dm::WBINS) {
+            const int c = q - Dm::TBINS;
+            if ((occW >> c) & 1ull) s.val[Dm::TCOLS + __popcll(occW & ((1ull << c) - 1ull))] = (unsigned char)c;
+        } else if (q < Dm::TBINS + Dm::WBINS + 5 * Dm::CBINS) {
+            const int k = q - Dm::TBINS - Dm::WBINS, wd = k / Dm::CBINS, c = k - wd * Dm::CBINS;
+            const unsigned int bits = (s.occ2[wd] & Dm::CMASK) | 1u;  // counts >= 1 in use, and 0 (a newcomer to the weekday)
+            if ((bits >> c) & 1u) s.val[Dm::VAL_C2 + wd * Dm::CBINS + __popc(bits & ((1u << c) - 1u))] = (unsigned char)c;
+        } else {
+            const int wd = q - Dm::TBINS - Dm::WBINS - 5 * Dm::CBINS;
+            s.val[Dm::VAL_N2 + wd] = (unsigned char)__popc((s.occ2[wd] & Dm::CMASK) | 1u);
         }
     }
     if (tid == 0) s.misc[ES_NSLOT] = fm.popc();

@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of scheduling-kernel build variants (alternative builds of the same library via CS_B200_LIB)
+# scheduling kernels: parity first, then device-timed rates (optionally against alternative builds via CS_B200_LIB)
+python -m pytest tests/test_es_gpu.py tests/test_fuzz_gpu.py tests/test_es_reference_mode_gpu.py tests/test_es_slots_gpu.py tests/test_ils_gpu.py -q -x -k "not nqueens and not nq_" 2>&1 | tail -1
 run() {  # workload, lib, launches
   for rep in 1 2; do
     CS_B200_LIB=$2 python bench.py --workload $1 --steps ${3:-8} --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
@@ -7,4 +8,4 @@ import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', 'lib=${2##*/}', '%.4g moves/s'%d['value'], '%.4f ms/step'%d['ms_per_step'])"
   done
 }
-for lib in "" "$@"; do run es2000 "$lib"; run es50 "$lib"; done
+for lib in "" "$@"; do run es2000 "$lib"; run es50 "$lib"; run es50x3 "$lib" 4; run es2000x3 "$lib" 2; done
