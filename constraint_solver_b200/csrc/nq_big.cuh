@@ -39,8 +39,7 @@ struct NqBig {
     unsigned long long* scored;       // [1] non-identity candidates scanned by this partition
     long long* key;                   // [1] packed (v, i, j) of this partition / after reduce
     int i_begin, i_end;               // this partition's column range
-    long long* dump;                  // debug: every candidate delta of the scanned columns ...
-    long long dump_base;              // ... written at (row-major pair index - dump_base): a band needs only its own entries
+    long long* dump;
     // packed-window fast scan (nqb_scan_packed_kernel): byte counters, 8 byte-shifted copies of
     // each diagonal array (copy c, byte y = D[y + c]; Q2's copies follow Q1's), rebuilt per step
     unsigned char* Q;                 // [16][ldb]
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(256) nqb_scan_kernel(NqBig b) {
                 if (!valid) x = NQ_INF;
                 if (DUMP) {
                     if (jin && j > i && i < b.i_end)
-                        b.dump[nq_swap_index(n, i, j) - b.dump_base] =
+                        b.dump[nq_swap_index(n, i, j)] =
                             (x >= NQ_INF) ? INT64_MAX
                                           : 2ll * (long long)(x + 4 - (int)__ldg(cc + i));
                 }
@@ -425,7 +424,7 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
                             const int i = i0 + 2 * p + h;
                             if (j > i && j < n && i >= b.i_begin && i < b.i_end) {
                                 const int zz = (int)(short)((z >> (16 * h)) & 0xffff);
-                                b.dump[nq_swap_index(n, i, j) - b.dump_base] = 2ll * (long long)(zz - NQBP_BIAS - (int)cb[i]);
+                                b.dump[nq_swap_index(n, i, j)] = 2ll * (long long)(zz - NQBP_BIAS - (int)cb[i]);
                             }
                         }
                     }
@@ -451,7 +450,7 @@ __global__ void __launch_bounds__(32 * NQBP_WARPS, 16 / NQBP_WARPS) nqb_scan_pac
                                 const int i = i0 + 2 * p + h;
                                 if (j > i && j < n && i >= b.i_begin && i < b.i_end) {
                                     const int zz = (int)(short)((z >> (16 * h)) & 0xffff);
-                                    b.dump[nq_swap_index(n, i, j) - b.dump_base] = 2ll * (long long)(zz - NQBP_BIAS - (int)cb[i]);
+                                    b.dump[nq_swap_index(n, i, j)] = 2ll * (long long)(zz - NQBP_BIAS - (int)cb[i]);
                                 }
                             }
                         }

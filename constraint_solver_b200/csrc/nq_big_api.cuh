@@ -112,10 +112,9 @@ bool nqb_is_perm(cs_nq_handle* h) {
 }
 
 // enqueue: c[], scan of this partition, row re-scan, packed key.  No host sync.
-void nqb_enqueue_scan(cs_nq_handle* h, bool perm, long long* dump, long long dump_base = 0) {
+void nqb_enqueue_scan(cs_nq_handle* h, bool perm, long long* dump) {
     NqBig b = h->big;
     b.dump = dump;
-    b.dump_base = dump_base;
     b.use_packed = (perm && b.n >= NQBP_MIN_N && !(h->cfg.flags & CS_NQ_FLAG_SCALAR)) ? 1 : 0;
     nqb_compute_c_kernel<<<nqb_grid(h, b.n), 256, 0, h->stream>>>(b);
     if (b.use_packed) {  // byte copies + largest line count, then the packed scan (no-op if a line is too long)
