@@ -13,6 +13,8 @@ OUT = os.path.join(ROOT, "gpurun_out")
 
 
 def bench_line(log):
+    if not os.path.exists(os.path.join(OUT, log)):
+        return {}
     for ln in reversed(open(os.path.join(OUT, log)).read().splitlines()):
         if ln.startswith("{"):
             return json.loads(ln)
