@@ -245,6 +245,8 @@ struct cs_nq_handle {
     // big-board (global-memory) mode: one instance, optional neighbourhood partition
     bool is_big = false;
     NqBig big{};
+    cudaStream_t l2_policy_stream = nullptr;  // stream the persisting-L2 window of the byte-copy tables is set on
+    bool l2_policy_set = false;
     unsigned int* d_best_rows32 = nullptr;
     NqBigStep* d_bstep = nullptr;
     NqBigStep* h_bstep = nullptr;       // pinned
@@ -307,6 +309,14 @@ void nq_free(cs_nq_handle* h) {
     cudaFree(h->d_bad);
     cudaFree(h->d_ls_rng);
     if (h->is_big) {
+        if (h->l2_policy_set && h->l2_policy_stream == h->stream && h->stream) {
+            // drop the persisting window before the tables go away (a hint; errors are not the caller's problem)
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaCtxResetPersistingL2Cache();
+            cudaGetLastError();
+        }
         cudaFree(h->big.rows);
         cudaFree(h->big.Q);
         cudaFree(h->big.cb);

@@ -111,8 +111,38 @@ bool nqb_is_perm(cs_nq_handle* h) {
     return st.is_perm != 0;
 }
 
+// Keep the byte-copy tables (2 x 16 copies, 64 MB at n = 10^6) resident in L2: a persisting access-policy
+// window over them on the handle's stream.  Without it the tables sit at the edge of what the two-die L2
+// holds and a step's DRAM re-reads vary 6-19 GB (225-246 ms) from run to run.  CS_NQB_L2_PERSIST=0 disables.
+void nqb_set_l2_policy(cs_nq_handle* h) {
+    if (h->l2_policy_set && h->l2_policy_stream == h->stream) return;
+    h->l2_policy_set = true;
+    h->l2_policy_stream = h->stream;
+    if (const char* e = std::getenv("CS_NQB_L2_PERSIST"))
+        if (std::atoi(e) == 0) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0 ||
+        prop.accessPolicyMaxWindowSize <= 0) {
+        cudaGetLastError();
+        return;
+    }
+    const size_t bytes = (size_t)2 * NQBP_COPIES * h->big.ldb;
+    const size_t persist = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = (void*)h->big.Q;
+    attr.accessPolicyWindow.num_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+    attr.accessPolicyWindow.hitRatio = (float)((double)persist / (double)attr.accessPolicyWindow.num_bytes);
+    if (attr.accessPolicyWindow.hitRatio > 1.0f) attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();  // a hint: never an error for the caller
+}
+
 // enqueue: c[], scan of this partition, row re-scan, packed key.  No host sync.
 void nqb_enqueue_scan(cs_nq_handle* h, bool perm, long long* dump) {
+    nqb_set_l2_policy(h);
     NqBig b = h->big;
     b.dump = dump;
     b.use_packed = (perm && b.n >= NQBP_MIN_N && !(h->cfg.flags & CS_NQ_FLAG_SCALAR)) ? 1 : 0;
