@@ -148,6 +148,9 @@ SIGNATURES = {
     "cs_nq_set_chains_async": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP]),
     "cs_nq_commit_chains": (C.c_int32, [_VP]),
     "cs_nq_step": (C.c_int32, [_VP, C.c_uint32, _P(CsStepStats)]),
+    "cs_nq_step_enqueue": (C.c_int32, [_VP, C.c_uint32]),
+    "cs_nq_step_wait": (C.c_int32, [_VP, _P(CsStepStats)]),
+    "cs_nq_exchange_select": (C.c_int32, [_VP, _VP, _VP, C.c_uint32]),
     "cs_nq_local_search": (C.c_int32, [_VP, C.c_uint64, C.c_uint64, _P(CsStepStats)]),
     "cs_nq_get_best_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, _VP]),
     "cs_nq_local_search_one": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint64, _VP, _P(C.c_int64)]),
@@ -188,6 +191,9 @@ SIGNATURES = {
     "cs_es_enumerate": (C.c_int32, [_VP, C.c_uint32, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_es_neighbourhood_deltas": (C.c_int32, [_VP, C.c_uint32, _VP, _VP, C.c_uint64, _P(C.c_uint64)]),
     "cs_es_step": (C.c_int32, [_VP, C.c_uint32, _P(CsEsStepStats)]),
+    "cs_es_step_enqueue": (C.c_int32, [_VP, C.c_uint32]),
+    "cs_es_step_wait": (C.c_int32, [_VP, _P(CsEsStepStats)]),
+    "cs_es_exchange_select": (C.c_int32, [_VP, _VP, _VP, C.c_uint32]),
     "cs_es_local_search": (C.c_int32, [_VP, C.c_uint64, C.c_uint64, _P(CsEsStepStats)]),
     "cs_es_get_best_chains": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
     "cs_es_local_search_one": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint64, _VP, _P(C.c_int64), _P(C.c_int64)]),

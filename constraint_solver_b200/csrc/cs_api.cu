@@ -242,6 +242,7 @@ struct cs_nq_handle {
     int* d_bad = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;  // chain scores valid
+    bool run_pending = false;  // a step was enqueued and not yet waited for
     // big-board (global-memory) mode: one instance, optional neighbourhood partition
     bool is_big = false;
     NqBig big{};
@@ -372,8 +373,8 @@ void nq_launch_step(cs_nq_handle* h, NqParams& p, int count) {
     CU(cudaGetLastError());
 }
 
-void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
-            unsigned long long allow, int ls_mode, cs_step_stats* stats) {
+void nq_run_enqueue(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
+                    unsigned long long allow, int ls_mode) {
     if (!h->scored) throw StateFail{"chains have no solution yet: call cs_nq_init_random or cs_nq_set_chains first"};
     NqParams p = nq_params(h, first, count);
     p.max_steps = max_steps;
@@ -387,7 +388,13 @@ void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, h->stream));
+    h->run_pending = true;
+}
+
+void nq_run_wait(cs_nq_handle* h, cs_step_stats* stats) {
+    if (!h->run_pending) throw StateFail{"no enqueued step to wait for"};
     CU(cudaStreamSynchronize(h->stream));
+    h->run_pending = false;
     if (stats) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -399,6 +406,12 @@ void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
         stats->device_ms = ms;
         stats->kernel_launches = 2;
     }
+}
+
+void nq_run(cs_nq_handle* h, int first, int count, unsigned long long max_steps,
+            unsigned long long allow, int ls_mode, cs_step_stats* stats) {
+    nq_run_enqueue(h, first, count, max_steps, allow, ls_mode);
+    nq_run_wait(h, stats);
 }
 
 // Returns true when some row value was outside [0, n): such rows are stored as 0, so the caller can
@@ -948,6 +961,41 @@ extern "C" int32_t cs_nq_step(cs_nq_handle* h, uint32_t n_steps, cs_step_stats* 
     return guarded(h, [&] {
         if (h->is_big) nqb_run(h, n_steps, 0, 0, stats);
         else nq_run(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0, stats);
+    });
+}
+
+extern "C" int32_t cs_nq_step_enqueue(cs_nq_handle* h, uint32_t n_steps) {
+    return guarded(h, [&] {
+        if (h->is_big) throw Unsupported{"the big-board step is a host loop: use cs_nq_part_scan / cs_nq_part_apply"};
+        nq_run_enqueue(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0);
+    });
+}
+
+extern "C" int32_t cs_nq_step_wait(cs_nq_handle* h, cs_step_stats* stats) {
+    return guarded(h, [&] { nq_run_wait(h, stats); });
+}
+
+// One block: the reduced key's owner writes its chain, everyone else zeros (cs_b200.h).
+__global__ void xchg_select_kernel(const long long* __restrict__ key, const uint16_t* __restrict__ rows,
+                                   size_t stride, unsigned chain_offset, unsigned n_chains, unsigned len,
+                                   uint16_t* __restrict__ elite, unsigned elite_len) {
+    const unsigned gid = (unsigned)((unsigned long long)*key & 0xFFFFFFFFull);
+    const bool mine = gid >= chain_offset && gid - chain_offset < n_chains;
+    const uint16_t* src = rows + (size_t)(mine ? gid - chain_offset : 0u) * stride;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < elite_len; i += gridDim.x * blockDim.x)
+        elite[i] = (mine && i < len) ? src[i] : (uint16_t)0;
+}
+
+extern "C" int32_t cs_nq_exchange_select(cs_nq_handle* h, const void* d_key, void* d_elite_u16, uint32_t elite_len) {
+    return guarded(h, [&] {
+        REQUIRE(d_key && d_elite_u16, "d_key / d_elite_u16 is NULL");
+        REQUIRE(!h->is_big, "not available on the big-board path");
+        if (elite_len == 0) return;
+        const unsigned grid = elite_len > 65536 ? 64u : (elite_len + 1023) / 1024;
+        xchg_select_kernel<<<grid, 1024, 0, h->stream>>>((const long long*)d_key, h->d_rows, (size_t)h->n_pad,
+                                                         (unsigned)h->cfg.chain_offset, h->cfg.n_chains, h->cfg.n,
+                                                         (uint16_t*)d_elite_u16, elite_len);
+        CU(cudaGetLastError());
     });
 }
 

@@ -48,6 +48,7 @@ struct cs_es_handle {
     bool async_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool scored = false;
+    bool run_pending = false;  // a step was enqueued and not yet waited for
     bool ref_mode = false;          // CS_ES_FLAG_REFERENCE_PROPOSER
     unsigned long long window = 100;  // window_size, examples/employee-scheduling/src/main.rs:26
     IlsHost ils;
@@ -197,8 +198,8 @@ void es_refresh_stats(cs_es_handle* h) {
     CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(EsStats), cudaMemcpyDeviceToHost, h->stream));
 }
 
-void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
-            unsigned long long allow, int ls_mode, cs_es_step_stats* stats) {
+void es_run_enqueue(cs_es_handle* h, int first, int count, unsigned long long max_steps,
+                    unsigned long long allow, int ls_mode) {
     if (!h->scored) throw StateFail{"chains have no solution yet: call cs_es_init_random or cs_es_set_chains first"};
     EsRun r;
     r.first = first;
@@ -215,7 +216,13 @@ void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->h_totals, h->d_totals, 2 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, h->stream));
+    h->run_pending = true;
+}
+
+void es_run_wait(cs_es_handle* h, cs_es_step_stats* stats) {
+    if (!h->run_pending) throw StateFail{"no enqueued step to wait for"};
     CU(cudaStreamSynchronize(h->stream));
+    h->run_pending = false;
     if (stats) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -229,6 +236,12 @@ void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
         stats->device_ms = ms;
         stats->kernel_launches = 2;
     }
+}
+
+void es_run(cs_es_handle* h, int first, int count, unsigned long long max_steps,
+            unsigned long long allow, int ls_mode, cs_es_step_stats* stats) {
+    es_run_enqueue(h, first, count, max_steps, allow, ls_mode);
+    es_run_wait(h, stats);
 }
 
 int es_index_of(cs_es_handle* h, int64_t id) {
@@ -846,6 +859,25 @@ extern "C" int32_t cs_es_neighbourhood_deltas(cs_es_handle* h, uint32_t chain, i
 
 extern "C" int32_t cs_es_step(cs_es_handle* h, uint32_t n_steps, cs_es_step_stats* stats) {
     return guarded(h, [&] { es_run(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0, stats); });
+}
+
+extern "C" int32_t cs_es_step_enqueue(cs_es_handle* h, uint32_t n_steps) {
+    return guarded(h, [&] { es_run_enqueue(h, 0, (int)h->cfg.n_chains, n_steps, 0, 0); });
+}
+
+extern "C" int32_t cs_es_step_wait(cs_es_handle* h, cs_es_step_stats* stats) {
+    return guarded(h, [&] { es_run_wait(h, stats); });
+}
+
+extern "C" int32_t cs_es_exchange_select(cs_es_handle* h, const void* d_key, void* d_elite_u16, uint32_t elite_len) {
+    return guarded(h, [&] {
+        REQUIRE(d_key && d_elite_u16, "d_key / d_elite_u16 is NULL");
+        if (elite_len == 0) return;
+        xchg_select_kernel<<<(elite_len + 1023) / 1024, 1024, 0, h->stream>>>(
+            (const long long*)d_key, h->d_a, (size_t)h->stride, (unsigned)h->cfg.chain_offset, h->cfg.n_chains,
+            (unsigned)h->stride, (uint16_t*)d_elite_u16, elite_len);
+        CU(cudaGetLastError());
+    });
 }
 
 extern "C" int32_t cs_es_local_search(cs_es_handle* h, uint64_t allow, uint64_t max_iterations,

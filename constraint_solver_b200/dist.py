@@ -90,13 +90,24 @@ class BestExchange:
         self.elite = torch.zeros((self.len + 1) & ~1, dtype=torch.int16, device=dev)  # even: reduced as int32
         ptr0, stride = eng.chain_device_ptr(0)
         self.rows_all = device_view(ptr0, (chains_per_rank, stride), "<i2", dev)
+        self.kbuf = torch.zeros(1, dtype=torch.int64, device=dev)
         self.reduced_key = None   # device tensor after sync_device()
         self.best_score = None
         self.best_chain = None
 
     def sync_device(self):
         """min-allreduce + elite delivery entirely on the device (no host sync); read the result
-        later with result()."""
+        later with result().  Four stream-ordered operations: key copy, min-all-reduce, the
+        library's owner-masked gather kernel (cs_*_exchange_select), sum-all-reduce of the elite."""
+        self.kbuf.copy_(self.key)
+        self.dist.all_reduce(self.kbuf, op=self.dist.ReduceOp.MIN)
+        self.eng.exchange_select(self.kbuf.data_ptr(), self.elite.data_ptr(), self.elite.numel())
+        self.dist.all_reduce(self.elite.view(torch.int32), op=self.dist.ReduceOp.SUM)
+        self.reduced_key = self.kbuf
+        return self.reduced_key
+
+    def sync_device_torch_ops(self):
+        """The same exchange written with torch ops only (what the gloo CPU tests run)."""
         self.reduced_key = exchange_best_device(self.dist, self.key, self.rows_all, self.elite, self.rank,
                                                 self.cpr)
         return self.reduced_key

@@ -244,6 +244,22 @@ class NQueensChains:
         self._check(self._lib.cs_nq_step(self._h, n_steps, C.byref(s)), "cs_nq_step")
         return self._stats(s)
 
+    def step_enqueue(self, n_steps: int = 1) -> None:
+        """Put n_steps chain-steps on the handle's stream and return without waiting."""
+        self._check(self._lib.cs_nq_step_enqueue(self._h, n_steps), "cs_nq_step_enqueue")
+
+    def step_wait(self) -> StepStats:
+        """Wait for the stream; stats of the last enqueued launch."""
+        s = L.CsStepStats()
+        self._check(self._lib.cs_nq_step_wait(self._h, C.byref(s)), "cs_nq_step_wait")
+        return self._stats(s)
+
+    def exchange_select(self, key_device_ptr: int, elite_device_ptr: int, elite_len: int) -> None:
+        """Owner-masked gather of the chain named by a DEVICE key (see cs_nq_exchange_select)."""
+        self._check(self._lib.cs_nq_exchange_select(self._h, C.c_void_p(key_device_ptr),
+                                                    C.c_void_p(elite_device_ptr), elite_len),
+                    "cs_nq_exchange_select")
+
     def local_search(self, allow_no_improvement_for: int, max_iterations: int) -> StepStats:
         s = L.CsStepStats()
         self._check(self._lib.cs_nq_local_search(self._h, allow_no_improvement_for, max_iterations,

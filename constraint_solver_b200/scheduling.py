@@ -242,6 +242,22 @@ class ScheduleChains:
         self._check(self._lib.cs_es_step(self._h, n_steps, C.byref(s)), "cs_es_step")
         return self._stats(s)
 
+    def step_enqueue(self, n_steps: int = 1) -> None:
+        """Put n_steps chain-steps on the handle's stream and return without waiting."""
+        self._check(self._lib.cs_es_step_enqueue(self._h, n_steps), "cs_es_step_enqueue")
+
+    def step_wait(self) -> EsStepStats:
+        """Wait for the stream; stats of the last enqueued launch."""
+        s = L.CsEsStepStats()
+        self._check(self._lib.cs_es_step_wait(self._h, C.byref(s)), "cs_es_step_wait")
+        return self._stats(s)
+
+    def exchange_select(self, key_device_ptr: int, elite_device_ptr: int, elite_len: int) -> None:
+        """Owner-masked gather of the chain named by a DEVICE key (see cs_es_exchange_select)."""
+        self._check(self._lib.cs_es_exchange_select(self._h, C.c_void_p(key_device_ptr),
+                                                    C.c_void_p(elite_device_ptr), elite_len),
+                    "cs_es_exchange_select")
+
     def local_search(self, allow_no_improvement_for: int, max_iterations: int) -> EsStepStats:
         s = L.CsEsStepStats()
         self._check(self._lib.cs_es_local_search(self._h, allow_no_improvement_for, max_iterations, C.byref(s)),

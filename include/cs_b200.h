@@ -195,6 +195,13 @@ int32_t cs_nq_set_window(cs_nq_handle* h, uint64_t window_size);
  * (local_search.rs:315-335 with window = whole neighbourhood).  A chain stops early when its
  * score is_best or its neighbourhood is empty.  stats may be NULL. */
 int32_t cs_nq_step(cs_nq_handle* h, uint32_t n_steps, cs_step_stats* stats);
+/* The same launch split in two so a multi-GPU driver never blocks the host between a step and the
+ * collective that follows it: _enqueue puts the n_steps chain-steps on the handle's stream and
+ * returns; _wait waits for the stream and reports the LAST enqueued launch (stats may be NULL).
+ * cs_nq_step == _enqueue + _wait.  Not available on the big-board path (its step is a host loop of
+ * scan + apply: use cs_nq_part_scan / cs_nq_part_apply). */
+int32_t cs_nq_step_enqueue(cs_nq_handle* h, uint32_t n_steps);
+int32_t cs_nq_step_wait(cs_nq_handle* h, cs_step_stats* stats);
 
 /* LocalSearch::execute, local-search/src/local_search.rs:301-342, on every chain from its
  * current state: bounded non-improving acceptance, best_solution bookkeeping (:326-328),
@@ -219,6 +226,12 @@ int32_t cs_nq_best(cs_nq_handle* h, int64_t* rows, int64_t* score, uint32_t* cha
  * int64, refreshed by step/local_search) so a host collective (NCCL min-allreduce) can run
  * on it without a host round trip. */
 int32_t cs_nq_best_key_device_ptr(cs_nq_handle* h, void** dptr);
+/* Elite delivery without a host round trip (the exchange of SURVEY 8e): d_key is a DEVICE int64 --
+ * the min-all-reduced best key, global chain id in its low 32 bits.  One kernel on the handle's
+ * stream writes d_elite_u16[0, elite_len): the rows of that chain when this handle owns it
+ * (chain_offset <= id < chain_offset + n_chains; zero past n), zeros otherwise -- so a sum
+ * all-reduce of the buffer lands the elite on every rank. */
+int32_t cs_nq_exchange_select(cs_nq_handle* h, const void* d_key, void* d_elite_u16, uint32_t elite_len);
 /* Overwrite one chain with a solution (elite broadcast target). */
 int32_t cs_nq_set_chain_u16_device(cs_nq_handle* h, uint32_t chain, const void* d_rows_u16);
 /* Device pointer to chain's rows (uint16 [n], padded stride available via *stride_elems). */
@@ -389,6 +402,9 @@ int32_t cs_es_set_window(cs_es_handle* h, uint64_t window_size);
 /* hot path: enumerate change + swap moves, delta-score the 8 constraints, lexicographic
  * (hard, soft, move id) argmin, accept (local_search.rs:315-335) */
 int32_t cs_es_step(cs_es_handle* h, uint32_t n_steps, cs_es_step_stats* stats);
+/* enqueue-only / wait halves of cs_es_step, as cs_nq_step_enqueue / cs_nq_step_wait */
+int32_t cs_es_step_enqueue(cs_es_handle* h, uint32_t n_steps);
+int32_t cs_es_step_wait(cs_es_handle* h, cs_es_step_stats* stats);
 /* LocalSearch::execute, local_search.rs:301-342 */
 int32_t cs_es_local_search(cs_es_handle* h, uint64_t allow_no_improvement_for,
                            uint64_t max_iterations, cs_es_step_stats* stats);
@@ -403,6 +419,8 @@ int32_t cs_es_best(cs_es_handle* h, int64_t* rows, int64_t* hard, int64_t* soft,
 /* device int64: (hard << 48) | (soft << 32) | global chain id */
 int32_t cs_es_best_key_device_ptr(cs_es_handle* h, void** dptr);
 int32_t cs_es_chain_device_ptr(cs_es_handle* h, uint32_t chain, void** dptr, uint32_t* n_slots);
+/* as cs_nq_exchange_select: the owning handle writes the chain's dense employee indices (uint16) */
+int32_t cs_es_exchange_select(cs_es_handle* h, const void* d_key, void* d_elite_u16, uint32_t elite_len);
 /* ILS shell, see cs_nq_ils_*; the perturbation may rewrite the phantom slot (lib.rs:599-608) */
 int32_t cs_es_ils_init(cs_es_handle* h, uint32_t best_solutions_capacity, uint32_t log_capacity);
 int32_t cs_es_ils_run(cs_es_handle* h, uint32_t rounds, uint64_t ls_max_iterations,

@@ -73,6 +73,9 @@ extern "C" {
                              cap: u64, n_out: *mut u64) -> i32;
     pub fn cs_nq_set_window(h: *mut cs_nq_handle, window_size: u64) -> i32;
     pub fn cs_nq_step(h: *mut cs_nq_handle, n_steps: u32, stats: *mut cs_step_stats) -> i32;
+    pub fn cs_nq_step_enqueue(h: *mut cs_nq_handle, n_steps: u32) -> i32;
+    pub fn cs_nq_step_wait(h: *mut cs_nq_handle, stats: *mut cs_step_stats) -> i32;
+    pub fn cs_nq_exchange_select(h: *mut cs_nq_handle, d_key: *const c_void, d_elite_u16: *mut c_void, elite_len: u32) -> i32;
     pub fn cs_nq_local_search(h: *mut cs_nq_handle, allow: u64, max_iterations: u64,
                               stats: *mut cs_step_stats) -> i32;
     pub fn cs_nq_local_search_one(h: *mut cs_nq_handle, start: *const i64, allow: u64,
@@ -104,6 +107,9 @@ extern "C" {
     pub fn cs_es_eval_moves(h: *mut cs_es_handle, chain: u32, moves: *const cs_es_move, n_moves: u64,
                             dhard: *mut i64, dsoft: *mut i64) -> i32;
     pub fn cs_es_step(h: *mut cs_es_handle, n_steps: u32, stats: *mut cs_es_step_stats) -> i32;
+    pub fn cs_es_step_enqueue(h: *mut cs_es_handle, n_steps: u32) -> i32;
+    pub fn cs_es_step_wait(h: *mut cs_es_handle, stats: *mut cs_es_step_stats) -> i32;
+    pub fn cs_es_exchange_select(h: *mut cs_es_handle, d_key: *const c_void, d_elite_u16: *mut c_void, elite_len: u32) -> i32;
     pub fn cs_es_set_chains_async(h: *mut cs_es_handle, first: u32, count: u32, rows: *const i64) -> i32;
     pub fn cs_es_commit_chains(h: *mut cs_es_handle) -> i32;
     pub fn cs_es_set_window(h: *mut cs_es_handle, window_size: u64) -> i32;
