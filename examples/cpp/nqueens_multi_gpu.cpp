@@ -2,8 +2,9 @@
 // GPU, one host thread.  Two modes, the two multi-GPU shapes of the north star:
 //   default        restart chains sharded across the GPUs (chain k of GPU g has global id
 //                  g * chains + k = its Philox stream); every --exchange steps the packed best
-//                  keys (score << 32 | global chain id) are min-all-reduced in place on the device
-//                  pointers and the elite board is broadcast from the GPU that owns it
+//                  keys (score << 32 | global chain id) are min-all-reduced on the device and the
+//                  elite board is delivered by cs_nq_exchange_select + a sum-all-reduce; the steps
+//                  are enqueued (cs_nq_step_enqueue), so the host never waits between them
 //   --partitioned  ONE large instance, every GPU holds a replica and scans a triangular-balanced
 //                  slice of the swap neighbourhood; per step one 8-byte min-all-reduce of the packed
 //                  (delta, i, j) key, every replica applies the same move -- no state crosses NVLink
@@ -16,7 +17,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "cs_b200.h"
@@ -90,44 +90,60 @@ int main(int argc, char** argv) {
             if (std::memcmp(r0.data(), rg.data(), sizeof(int64_t) * n) != 0) { std::fprintf(stderr, "replica %d diverged\n", g); return 1; }
         }
     } else {
-        std::vector<void*> key(G);
-        std::vector<void*> elite(G);
+        // One host thread drives every GPU and never waits inside a step: cs_nq_step_enqueue puts the
+        // chain-steps on the handle's stream, the exchange (min-all-reduce of the packed key, the
+        // library's owner-masked gather, sum-all-reduce of the elite) follows on the same streams,
+        // and cs_nq_step_wait collects the statistics afterwards.
+        std::vector<void*> key(G), kbuf(G), elite(G);
         uint32_t stride = 0;
         for (int g = 0; g < G; ++g) {
             CS(h[g], cs_nq_best_key_device_ptr(h[g], &key[g]));
             void* p = nullptr;
             CS(h[g], cs_nq_chain_device_ptr(h[g], 0, &p, &stride));
             CK(cudaSetDevice(g));
-            CK(cudaMalloc(&elite[g], (size_t)stride * sizeof(uint16_t)));
+            CK(cudaMalloc(&kbuf[g], sizeof(long long)));
+            CK(cudaMalloc(&elite[g], (size_t)stride * sizeof(uint16_t)));  // the stride is even: reduced as int32
         }
         for (uint32_t s = 0; s < steps; ++s) {
-            // cs_nq_step returns when its GPU is done, so the GPUs are driven by one thread each
-            // (a handle is Send-not-Sync: one thread at a time, any thread)
-            std::vector<cs_step_stats> st(G);
-            std::vector<std::thread> th;
-            for (int g = 0; g < G; ++g)
-                th.emplace_back([&, g] { CK(cudaSetDevice(g)); CS(h[g], cs_nq_step(h[g], 1, &st[g])); });
-            for (auto& t : th) t.join();
-            for (int g = 0; g < G; ++g) moves += st[g].moves_scored;
-            if ((s + 1) % exchange == 0 || s + 1 == steps) {
+            for (int g = 0; g < G; ++g) CS(h[g], cs_nq_step_enqueue(h[g], 1));
+            const bool xchg = (s + 1) % exchange == 0 || s + 1 == steps;
+            if (xchg) {
+                for (int g = 0; g < G; ++g) {
+                    CK(cudaSetDevice(g));
+                    CK(cudaMemcpyAsync(kbuf[g], key[g], sizeof(long long), cudaMemcpyDeviceToDevice, stream[g]));
+                }
                 NK(ncclGroupStart());
-                for (int g = 0; g < G; ++g) NK(ncclAllReduce(key[g], key[g], 1, ncclInt64, ncclMin, comm[g], stream[g]));
+                for (int g = 0; g < G; ++g) NK(ncclAllReduce(kbuf[g], kbuf[g], 1, ncclInt64, ncclMin, comm[g], stream[g]));
                 NK(ncclGroupEnd());
+                for (int g = 0; g < G; ++g) CS(h[g], cs_nq_exchange_select(h[g], kbuf[g], elite[g], stride));
+                NK(ncclGroupStart());  // the owner contributes the chain, everyone else zeros
+                for (int g = 0; g < G; ++g) NK(ncclAllReduce(elite[g], elite[g], stride / 2, ncclInt32, ncclSum, comm[g], stream[g]));
+                NK(ncclGroupEnd());
+            }
+            for (int g = 0; g < G; ++g) {
+                cs_step_stats st{};
+                CS(h[g], cs_nq_step_wait(h[g], &st));
+                moves += st.moves_scored;
+            }
+            if (xchg) {
                 long long k = 0;
                 CK(cudaSetDevice(0));
-                CK(cudaMemcpyAsync(&k, key[0], sizeof k, cudaMemcpyDeviceToHost, stream[0]));
-                CK(cudaStreamSynchronize(stream[0]));
+                CK(cudaMemcpy(&k, kbuf[0], sizeof k, cudaMemcpyDeviceToHost));
                 best = k >> 32;
+                // every GPU now holds the same elite: check it against the owner's chain
                 const uint32_t gid = (uint32_t)(k & 0xffffffffll), owner = gid / chains, local = gid % chains;
-                void* src = nullptr;
-                CS(h[owner], cs_nq_chain_device_ptr(h[owner], local, &src, &stride));
-                NK(ncclGroupStart());  // elite broadcast from the owning GPU (n x 2 bytes)
-                for (int g = 0; g < G; ++g)
-                    NK(ncclBroadcast(g == (int)owner ? src : elite[g], elite[g], (size_t)stride * 2, ncclUint8, (int)owner, comm[g], stream[g]));
-                NK(ncclGroupEnd());
-                for (int g = 0; g < G; ++g) { CK(cudaSetDevice(g)); CK(cudaStreamSynchronize(stream[g])); }
+                std::vector<int64_t> row(n);
+                CS(h[owner], cs_nq_get_chains(h[owner], local, 1, row.data()));
+                std::vector<uint16_t> e(stride);
+                for (int g = 0; g < G; ++g) {
+                    CK(cudaSetDevice(g));
+                    CK(cudaMemcpy(e.data(), elite[g], (size_t)stride * 2, cudaMemcpyDeviceToHost));
+                    for (uint32_t i = 0; i < n; ++i)
+                        if ((int64_t)e[i] != row[i]) { std::fprintf(stderr, "elite on GPU %d differs from its owner's chain\n", g); return 1; }
+                }
             }
         }
+        for (int g = 0; g < G; ++g) { CK(cudaSetDevice(g)); CK(cudaFree(kbuf[g])); }
         for (int g = 0; g < G; ++g) { CK(cudaSetDevice(g)); CK(cudaFree(elite[g])); }
     }
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
