@@ -11,6 +11,7 @@ struct cs_es_handle {
     int D = 0, S = 1, T = 0;  // days, shifts per day, scored slots (T = D * S)
     int W = 1;                // 64-bit words per slot mask
     bool multi = false;       // slot-generalised extension (S > 1 or a skill table with a gap)
+    int wd = 1;               // words that hold the day-indexed sets: ceil(D / 64) <= W
     int dp = 0;               // T rounded up to 4 (stride of the per-slot constant tables)
     int stride = 0;           // T + 1 slots (phantom last)
     int threads = 128;
@@ -163,6 +164,22 @@ void es_check_range(cs_es_handle* h, uint32_t first, uint32_t count) {
             "chain range outside [0, n_chains)");
 }
 
+// the step kernel of this handle: the reference proposer's variant, or the full scan with its day-indexed
+// sets cut to ceil(days / 64) words (several shifts per day: fewer days than slots)
+template <int W, bool MULTI>
+void (*es_step_fn(const cs_es_handle* h))(EsParamsT<W>) {
+    if constexpr (!MULTI) {
+        if (h->ref_mode) return es_step_kernel<W, false, true>;
+        return es_step_kernel<W, false, false>;
+    } else {
+        if (h->wd == 1) return es_step_kernel<W, true, false, 1>;
+        if constexpr (W >= 3) {
+            if (h->wd == 2) return es_step_kernel<W, true, false, 2>;
+        }
+        return es_step_kernel<W, true, false, W>;
+    }
+}
+
 void es_launch_step(cs_es_handle* h, int grid, const EsRun& r) {
     es_dispatch(h, [&](auto w, auto m) {
         constexpr int W = decltype(w)::value;
@@ -174,8 +191,7 @@ void es_launch_step(cs_es_handle* h, int grid, const EsRun& r) {
         p.dump_h = r.dump_h;
         p.dump_s = r.dump_s;
         p.skip = r.skip;
-        if (!MULTI && h->ref_mode) es_step_kernel<W, false, true><<<grid, h->threads, h->smem, h->stream>>>(p);
-        else es_step_kernel<W, MULTI, false><<<grid, h->threads, h->smem, h->stream>>>(p);
+        es_step_fn<W, MULTI>(h)<<<grid, h->threads, h->smem, h->stream>>>(p);
     });
     CU(cudaGetLastError());
 }
@@ -367,6 +383,7 @@ extern "C" int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* emplo
     h->T = T;
     h->W = (T + 63) / 64;
     h->multi = multi;
+    h->wd = (D + 63) / 64;
     h->dp = (T + 3) & ~3;
     const int32_t rc = guarded(h, [&] {
         const int W = h->W, dp = h->dp;
@@ -481,11 +498,10 @@ extern "C" int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* emplo
         es_dispatch(h, [&](auto w, auto m) {
             constexpr int W_ = decltype(w)::value;
             constexpr bool MULTI = decltype(m)::value;
-            allow_max_smem(es_step_kernel<W_, MULTI, false>, prop);
-            if (!MULTI) allow_max_smem(es_step_kernel<W_, false, true>, prop);
+            allow_max_smem(es_step_fn<W_, MULTI>(h), prop);
             allow_max_smem(es_rescore_kernel<W_, MULTI>, prop);
             allow_max_smem(es_eval_kernel<W_, MULTI>, prop);
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_kernel<W_, MULTI, false>, h->threads,
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, es_step_fn<W_, MULTI>(h), h->threads,
                                                              h->smem));
         });
         if (per_sm < 1) per_sm = 1;

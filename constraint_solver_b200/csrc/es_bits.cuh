@@ -125,6 +125,17 @@ struct Bits {
     __device__ __forceinline__ int rank_below(int f) const { return (*this & lowmask(f)).popc(); }
 };
 
+// the low WD words of a wider set known to be empty above them (day-indexed sets of a rota with at most
+// 64 * WD days, stored in slot-width words): arithmetic on Bits<WD> instead of Bits<W>
+template <int WD, int W>
+__host__ __device__ __forceinline__ Bits<WD> bits_lo(const Bits<W>& a) {
+    static_assert(WD >= 1 && WD <= W, "WD words of a W-word set");
+    Bits<WD> r;
+#pragma unroll
+    for (int i = 0; i < WD; ++i) r.w[i] = a.w[i];
+    return r;
+}
+
 // set bit d of a bitset in shared memory: a NATIVE 32-bit atomic on the half-word that holds it (a 64-bit
 // shared-memory atomicOr compiles to a compare-and-swap loop; ncu showed it at 8 % of the instructions
 // and 16 % of the stall samples of the small-rota step)

@@ -578,7 +578,7 @@ __device__ __forceinline__ int es_avoid_bits(const EsSmemT<W>& s, int slot, int 
 
 // Once per chain-step (masks + tallies must be current).  Everything is per slot or per
 // (slot, value in use): no loop over the employee table.
-template <int W, bool MULTI>
+template <int W, bool MULTI, int WD = W>
 __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits<W>* __restrict__ hol,
                            const Bits<W>* __restrict__ unsk) {
     typedef EsDim<W> Dm;
@@ -643,9 +643,10 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
             const int slot = s.dslot[d];
             const Bits<W> m = s.smask[slot];
             const EsEq<W> q = es_eq(s, slot);
-            int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() + (q[1] & s.cont14[d]).popc();
+            int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() +
+                        (bits_lo<WD>(q[1]) & bits_lo<WD>(s.cont14[d])).popc();
             if (MULTI) lossH += (m & s.partx[d]).popc();
-            const int lossS = (q[3] & s.cont7[d]).popc();
+            const int lossS = (bits_lo<WD>(q[3]) & bits_lo<WD>(s.cont7[d])).popc();
             s.base[d] = ((unsigned)(0x8000 - lossH) << 16) | (unsigned)(0x8000 - lossS);
             // an absent receiver: no pairs, no window counts, zero slots anywhere
             const int to = s.dayb[d], wo = s.dayb[s.dp + d], wd = s.dwd[d];
@@ -728,14 +729,18 @@ __device__ __forceinline__ unsigned int es_w_to_v(unsigned int w) {
 
 // change: slot d goes to the PRESENT employee of owner `slot` (not the slot's current one).  ga = the
 // receiver-side parts (hard gain, S1 gain, S2 delta) packed for the swap pass.
-template <int W, bool MULTI>
+// WD: words that hold the DAY-indexed sets (window starts: cont14 / cont7 / the "count == k" planes).  With
+// several shifts per day a rota of T <= 64 W slots has only T / S days, so those sets are empty above word
+// WD = ceil(D / 64) and their popcounts run on WD words instead of W.
+template <int W, bool MULTI, int WD = W>
 __device__ __forceinline__ unsigned int es_change_present_v(const EsSmemT<W>& s, int d, int slot, unsigned int& ga) {
     typedef EsDim<W> Dm;
     const Bits<W> m = s.smask[slot];
     const EsEq<W> q = es_eq(s, slot);
-    int gh = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() + (q[0] & s.cont14[d]).popc();
+    int gh = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() +
+             (bits_lo<WD>(q[0]) & bits_lo<WD>(s.cont14[d])).popc();
     if (MULTI) gh += (m & s.partx[d]).popc();
-    const int gs = (q[2] & s.cont7[d]).popc();
+    const int gs = (bits_lo<WD>(q[2]) & bits_lo<WD>(s.cont7[d])).popc();
     const int cn = (m & s.wdm[d]).popc();
     const int s2 = (int)s.s2t[d * Dm::CBINS + cn];
     ga = (unsigned)gh | ((unsigned)gs << 5) | ((unsigned)(s2 + 32) << 8);
@@ -801,7 +806,7 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmemT<W>& s, const EsC
 // transfers, slot d1 -> e2 and slot d2 -> e1; their tabulated gains/losses are exact except where
 // both slots meet -- the H2/H3 (and same-day) pair (d1, d2) itself and the windows holding BOTH
 // days, whose counts do not change.
-template <int W, bool MULTI>
+template <int W, bool MULTI, int WD = W>
 __device__ __forceinline__ unsigned int es_swap_from_table(const EsSmemT<W>& s, int d1, int d2) {
     typedef EsDim<W> Dm;
     const int s1 = s.dslot[d1], s2 = s.dslot[d2];
@@ -814,12 +819,14 @@ __device__ __forceinline__ unsigned int es_swap_from_table(const EsSmemT<W>& s, 
         if (s.part[d1].test(d2)) dh -= 2;
         if (MULTI && s.partx[d1].test(d2)) dh -= 2;
         const EsEq<W> q1 = es_eq(s, s1), q2 = es_eq(s, s2);
-        const Bits<W> both14 = s.cont14[d1] & s.cont14[d2];
+        const Bits<WD> both14 = bits_lo<WD>(s.cont14[d1]) & bits_lo<WD>(s.cont14[d2]);
         if (both14.any())
-            dh += (q1[1] & both14).popc() - (q1[0] & both14).popc() + (q2[1] & both14).popc() - (q2[0] & both14).popc();
-        const Bits<W> both7 = s.cont7[d1] & s.cont7[d2];
+            dh += (bits_lo<WD>(q1[1]) & both14).popc() - (bits_lo<WD>(q1[0]) & both14).popc() +
+                  (bits_lo<WD>(q2[1]) & both14).popc() - (bits_lo<WD>(q2[0]) & both14).popc();
+        const Bits<WD> both7 = bits_lo<WD>(s.cont7[d1]) & bits_lo<WD>(s.cont7[d2]);
         if (both7.any())
-            ds += (q1[3] & both7).popc() - (q1[2] & both7).popc() + (q2[3] & both7).popc() - (q2[2] & both7).popc();
+            ds += (bits_lo<WD>(q1[3]) & both7).popc() - (bits_lo<WD>(q1[2]) & both7).popc() +
+                  (bits_lo<WD>(q2[3]) & both7).popc() - (bits_lo<WD>(q2[2]) & both7).popc();
     }
     const int wd1 = s.dwd[d1], wd2 = s.dwd[d2];
     if (wd1 != wd2) {
@@ -866,7 +873,7 @@ __device__ __forceinline__ long long es_block_min(long long key, u64* red) {
 //   B  change moves to ABSENT employees   (thread per employee, loop over slots; the value is the
 //      per-slot table entry plus the employee's holiday / skill bits, tracked with one min per candidate)
 //   C  swaps
-template <int W, bool MULTI, bool DUMP>
+template <int W, bool MULTI, bool DUMP, int WD = W>
 __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT<W>& K,
                                              const Bits<W>* __restrict__ hol, const Bits<W>* __restrict__ unsk,
                                              const uint16_t* __restrict__ scan, long long* dump_h,
@@ -883,7 +890,7 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
             const int id = d * E + (int)s.semp[slot];
             if ((int)s.dslot[d] != slot) {
                 unsigned int ga;
-                const unsigned int v = es_change_present_v<W, MULTI>(s, d, slot, ga);
+                const unsigned int v = es_change_present_v<W, MULTI, WD>(s, d, slot, ga);
                 s.ga[d * s.ns + slot] = (uint16_t)ga;
                 const long long k2 = es_key(v, id);
                 key = k2 < key ? k2 : key;
@@ -973,7 +980,7 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
             const int dd = scan[r], d1 = dd >> 8, d2 = dd & 0xff;
             const int id = n_change + es_tri_index(T, d1, d2);
             if (s.dslot[d1] != s.dslot[d2]) {
-                const unsigned int v = es_swap_from_table<W, MULTI>(s, d1, d2);
+                const unsigned int v = es_swap_from_table<W, MULTI, WD>(s, d1, d2);
                 const long long k2 = es_key(v, id);
                 key = k2 < key ? k2 : key;
                 if (DUMP) {
@@ -1136,7 +1143,7 @@ __device__ __forceinline__ void es_load_consts(const EsSmemT<W>& s, const EsCons
 #define ES_LB_THREADS(W, MULTI) (((W) == 1 && !(MULTI)) ? 256 : 512)
 #define ES_LB_BLOCKS(W, MULTI) (((W) == 1 && !(MULTI)) ? 4 : 1)
 
-template <int W, bool MULTI, bool REF>
+template <int W, bool MULTI, bool REF, int WD = W>
 __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI)) es_step_kernel(EsParamsT<W> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EsConstT<W>& K = p.K;
@@ -1177,7 +1184,7 @@ __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI
                 best_s = 0;
                 break;
             }
-            es_prepare<W, MULTI>(s, K, p.hol, p.unsk);
+            es_prepare<W, MULTI, WD>(s, K, p.hol, p.unsk);
             // non-identity candidates: every (slot, employee != current) + every slot pair held by
             // two different employees -- each of them is evaluated by es_scan
             long long key;
@@ -1187,8 +1194,8 @@ __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI
                 scored += nsc;
             } else {
                 scored += (unsigned long long)(n_change - T) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
-                key = p.dump_h ? es_scan<W, MULTI, true>(s, K, p.hol, p.unsk, p.tri_scan, p.dump_h, p.dump_s)
-                               : es_scan<W, MULTI, false>(s, K, p.hol, p.unsk, p.tri_scan, nullptr, nullptr);
+                key = p.dump_h ? es_scan<W, MULTI, true, WD>(s, K, p.hol, p.unsk, p.tri_scan, p.dump_h, p.dump_s)
+                               : es_scan<W, MULTI, false, WD>(s, K, p.hol, p.unsk, p.tri_scan, nullptr, nullptr);
                 key = es_block_min(key, s.red);
             }
             if (p.dump_h) break;

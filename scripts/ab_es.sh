@@ -8,4 +8,5 @@ import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', 'lib=${2##*/}', '%.4g moves/s'%d['value'], '%.4f ms/step'%d['ms_per_step'])"
   done
 }
-for lib in "" "$@"; do run es2000 "$lib"; run es50 "$lib"; run es50x3 "$lib" 4; run es2000x3 "$lib" 2; done
+WLS=${WLS:-es2000 es50 es50x3 es2000x3}
+for lib in "" "$@"; do for wl in $WLS; do run $wl "$lib" $([ $wl = es2000x3 ] && echo 2 || ([ $wl = es50x3 ] && echo 4 || echo 8)); done; done
