@@ -25,6 +25,7 @@ struct cs_es_handle {
     uint16_t* d_best_a = nullptr;
     u64* d_hol = nullptr;     // [E][W] holiday slot mask per employee
     u64* d_unsk = nullptr;    // [E][W] multi: slots whose shift kind the employee is not qualified for
+    u64* d_cnt2 = nullptr;    // [E][2W] multi: holiday + unskilled bits per slot as 2-bit counts (pass B)
     u64* d_slotc = nullptr;   // [4][dp][W] PART, CONT14, CONT7, PARTX
     uint16_t* d_tri = nullptr;  // [2][n_swap] (d1 << 8 | d2): enumeration order, then scan order
     size_t n_swap = 0;
@@ -104,6 +105,7 @@ EsParamsT<W> es_params(cs_es_handle* h, int first, int count) {
     p.best_a = h->d_best_a;
     p.hol = (const Bits<W>*)h->d_hol;
     p.unsk = (const Bits<W>*)h->d_unsk;
+    p.cnt2 = h->d_cnt2;
     p.slotc = (const Bits<W>*)h->d_slotc;
     p.tri = h->d_tri;
     p.tri_scan = h->d_tri + h->n_swap;
@@ -137,6 +139,7 @@ void es_free(cs_es_handle* h) {
     cudaFree(h->d_best_a);
     cudaFree(h->d_hol);
     cudaFree(h->d_unsk);
+    cudaFree(h->d_cnt2);
     cudaFree(h->d_slotc);
     cudaFree(h->d_tri);
     cudaFree(h->d_st);
@@ -532,7 +535,18 @@ extern "C" int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* emplo
         CU(cudaEventCreate(&h->ev0));
         CU(cudaEventCreate(&h->ev1));
         CU(cudaMemcpy(h->d_hol, hol.data(), hol.size() * sizeof(u64), cudaMemcpyHostToDevice));
-        if (multi) CU(cudaMemcpy(h->d_unsk, unsk.data(), unsk.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        if (multi) {
+            CU(cudaMemcpy(h->d_unsk, unsk.data(), unsk.size() * sizeof(u64), cudaMemcpyHostToDevice));
+            std::vector<u64> cnt2((size_t)E * 2 * W, 0ull);  // slot t -> bits 2t, 2t+1 = holiday bit + unskilled bit
+            for (int e = 0; e < E; ++e)
+                for (int t = 0; t < T; ++t) {
+                    const u64 c = ((hol[(size_t)e * W + (t >> 6)] >> (t & 63)) & 1ull) +
+                                  ((unsk[(size_t)e * W + (t >> 6)] >> (t & 63)) & 1ull);
+                    cnt2[(size_t)e * 2 * W + (t >> 5)] |= c << (2 * (t & 31));
+                }
+            CU(cudaMalloc(&h->d_cnt2, cnt2.size() * sizeof(u64)));
+            CU(cudaMemcpy(h->d_cnt2, cnt2.data(), cnt2.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        }
         CU(cudaMemcpy(h->d_slotc, slotc.data(), slotc.size() * sizeof(u64), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->d_tri, tri.data(), tri.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CU(cudaMemsetAsync(h->d_a, 0, nc * h->stride * sizeof(uint16_t), h->stream));

@@ -93,6 +93,7 @@ struct EsParamsT {
     uint16_t* best_a;
     const Bits<W>* hol;    // [E] holiday slot-mask per employee
     const Bits<W>* unsk;   // [E] MULTI: slots whose shift kind the employee is NOT qualified for
+    const u64* cnt2;       // [E][2 W] MULTI: holiday + unskilled bits of every slot as a 2-bit count (pass B's addend)
     const Bits<W>* slotc;  // [4][dp]: PART (H2/H3 partner slots), CONT14, CONT7 (window starts holding the slot's day), PARTX (same-day slots)
     const uint16_t* tri;   // [n_swap] (d1 << 8 | d2), enumeration order; then the same pairs in scan order
     const uint16_t* tri_scan;
@@ -876,6 +877,7 @@ __device__ __forceinline__ long long es_block_min(long long key, u64* red) {
 template <int W, bool MULTI, bool DUMP, int WD = W>
 __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT<W>& K,
                                              const Bits<W>* __restrict__ hol, const Bits<W>* __restrict__ unsk,
+                                             const u64* __restrict__ cnt2,
                                              const uint16_t* __restrict__ scan, long long* dump_h,
                                              long long* dump_s) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -917,16 +919,43 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
         constexpr unsigned int HB = 1u << ES_W_DH;
         for (int e = tid; e < E; e += nt) {
             if (s.mask[e].any()) continue;
-            const Bits<W> h = hol[e];
-            Bits<W> u = Bits<W>::zero();
-            if (MULTI) u = unsk[e];
             unsigned int w = 0xffffffffu;
+            if (MULTI) {
+                // the holiday and missing-skill bits of a slot arrive as one 2-bit count (cnt2, built with the
+                // handle): value = baseW + count << ES_W_DH, a mask and a multiply-add per candidate
+                const u64* c2 = cnt2 + (size_t)e * (2 * W);
 #pragma unroll
-            for (int i = 0; i < W; ++i) {
-                const int lim = min(T - 64 * i, 64);
-                for (int d0 = 0; d0 < lim; d0 += 4) {
-                    unsigned int w0, w1, w2, w3;
-                    if (!MULTI) {  // the group's values for this employee's holiday pattern: one table row per load
+                for (int g = 0; g < 2 * W; ++g) {
+                    const int lim = min(T - 32 * g, 32);
+                    if (lim <= 0) break;
+                    const u64 cw = c2[g];
+                    for (int d0 = 0; d0 < lim; d0 += 4) {
+                        const uint4 b = bw4[(32 * g + d0) >> 2];
+                        const unsigned int x = (unsigned int)(cw >> (2 * d0));  // counts of slots d0..d0+3, 2 bits each
+                        const unsigned int w0 = b.x + (x & 0x03u) * HB;
+                        const unsigned int w1 = b.y + (x & 0x0cu) * (HB >> 2);
+                        const unsigned int w2 = b.z + (x & 0x30u) * (HB >> 4);
+                        const unsigned int w3 = b.w + (x & 0xc0u) * (HB >> 6);
+                        w = __vimin3_u32(w, w0, w1);
+                        w = __vimin3_u32(w, w2, w3);
+                        if (DUMP) {
+                            const unsigned int ww[4] = {w0, w1, w2, w3};
+                            for (int j = 0; j < 4 && 32 * g + d0 + j < T; ++j) {
+                                const unsigned int v = es_w_to_v(ww[j]);
+                                dump_h[(32 * g + d0 + j) * E + e] = es_v_dh(v);
+                                dump_s[(32 * g + d0 + j) * E + e] = es_v_ds(v);
+                            }
+                        }
+                    }
+                }
+            } else {
+                const Bits<W> h = hol[e];
+#pragma unroll
+                for (int i = 0; i < W; ++i) {
+                    const int lim = min(T - 64 * i, 64);
+                    for (int d0 = 0; d0 < lim; d0 += 4) {
+                        // the group's values for this employee's holiday pattern: one table row per load
+                        unsigned int w0, w1, w2, w3;
                         const unsigned int x = (unsigned int)(h.w[i] >> d0);
                         if (ES_BQ == 4) {
                             const uint4 b = ((const uint4*)s.bwq)[((64 * i + d0) >> 2) * 16 + (x & 15u)];
@@ -942,23 +971,15 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
                             w2 = b1.x;
                             w3 = b1.y;
                         }
-                    } else {
-                        const uint4 b = bw4[(64 * i + d0) >> 2];
-                        const unsigned int x = (unsigned int)(h.w[i] >> d0);  // holiday bits of slots d0..d0+3
-                        const unsigned int y = (unsigned int)(u.w[i] >> d0);  // missing-skill bits
-                        w0 = b.x + ((x << ES_W_DH) & HB) + ((y << ES_W_DH) & HB);
-                        w1 = b.y + ((x << (ES_W_DH - 1)) & HB) + ((y << (ES_W_DH - 1)) & HB);
-                        w2 = b.z + ((x << (ES_W_DH - 2)) & HB) + ((y << (ES_W_DH - 2)) & HB);
-                        w3 = b.w + ((x << (ES_W_DH - 3)) & HB) + ((y << (ES_W_DH - 3)) & HB);
-                    }
-                    w = __vimin3_u32(w, w0, w1);
-                    w = __vimin3_u32(w, w2, w3);
-                    if (DUMP) {
-                        const unsigned int ww[4] = {w0, w1, w2, w3};
-                        for (int j = 0; j < 4 && 64 * i + d0 + j < T; ++j) {
-                            const unsigned int v = es_w_to_v(ww[j]);
-                            dump_h[(64 * i + d0 + j) * E + e] = es_v_dh(v);
-                            dump_s[(64 * i + d0 + j) * E + e] = es_v_ds(v);
+                        w = __vimin3_u32(w, w0, w1);
+                        w = __vimin3_u32(w, w2, w3);
+                        if (DUMP) {
+                            const unsigned int ww[4] = {w0, w1, w2, w3};
+                            for (int j = 0; j < 4 && 64 * i + d0 + j < T; ++j) {
+                                const unsigned int v = es_w_to_v(ww[j]);
+                                dump_h[(64 * i + d0 + j) * E + e] = es_v_dh(v);
+                                dump_s[(64 * i + d0 + j) * E + e] = es_v_ds(v);
+                            }
                         }
                     }
                 }
@@ -1194,8 +1215,8 @@ __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI
                 scored += nsc;
             } else {
                 scored += (unsigned long long)(n_change - T) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
-                key = p.dump_h ? es_scan<W, MULTI, true, WD>(s, K, p.hol, p.unsk, p.tri_scan, p.dump_h, p.dump_s)
-                               : es_scan<W, MULTI, false, WD>(s, K, p.hol, p.unsk, p.tri_scan, nullptr, nullptr);
+                key = p.dump_h ? es_scan<W, MULTI, true, WD>(s, K, p.hol, p.unsk, p.cnt2, p.tri_scan, p.dump_h, p.dump_s)
+                               : es_scan<W, MULTI, false, WD>(s, K, p.hol, p.unsk, p.cnt2, p.tri_scan, nullptr, nullptr);
                 key = es_block_min(key, s.red);
             }
             if (p.dump_h) break;
