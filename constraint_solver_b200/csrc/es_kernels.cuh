@@ -139,6 +139,7 @@ struct EsSmemT {
     Bits<W>* sunsk;     // [NS] MULTI: its unskilled-slot mask
     uint16_t* semp;     // [NS] its employee index
     unsigned char* srk;    // [NS][2] rank of its total / weekend count among the values in use
+    unsigned char* swd;    // [NS][8] W > 1: its slots per weekday Mon..Fri (entries 5..7 stay 0: weekend slots carry no S2 term)
     unsigned char* val;    // [VAL_BYTES] rank -> value lists
     unsigned char* dwd;    // [DP] weekday of the slot's day (0 = Monday)
     unsigned char* sday;   // [DP] day of the slot
@@ -156,7 +157,7 @@ struct EsSmemT {
 };
 
 struct EsLayout {
-    size_t mask, a, hist, occ, occT, occW, fmask, misc, red, slot, eq, smask, shol, sunsk, semp, srk, val, dwd, sday,
+    size_t mask, a, hist, occ, occT, occW, fmask, misc, red, slot, eq, smask, shol, sunsk, semp, srk, swd, val, dwd, sday,
         dslot, dayb, base, baseW, bwq, s2t, s3t, s4t, s4s, ga, total;
     int ns, dp;
 };
@@ -190,6 +191,7 @@ __host__ __device__ inline EsLayout es_layout(int T, int E) {
     L.a = o;       o = es_align(o + (size_t)(T + 1) * 2, 8);
     L.semp = o;    o = es_align(o + (size_t)L.ns * 2, 8);
     L.srk = o;     o = es_align(o + (size_t)L.ns * 2, 8);
+    L.swd = o;     o += W > 1 ? (size_t)L.ns * 8 : 0;  // one word: the popcount itself is as cheap as the lookup
     L.val = o;     o = es_align(o + Dm::VAL_BYTES, 8);
     L.dwd = o;     o += dp;
     L.sday = o;    o += dp;
@@ -238,6 +240,7 @@ __device__ __forceinline__ EsSmemT<W> es_carve(unsigned char* p, int T, int E) {
     s.sunsk = (Bits<W>*)(p + L.sunsk);
     s.semp = (uint16_t*)(p + L.semp);
     s.srk = p + L.srk;
+    s.swd = p + L.swd;
     s.val = p + L.val;
     s.dwd = p + L.dwd;
     s.sday = p + L.sday;
@@ -569,11 +572,19 @@ __device__ void es_build(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits<W
     __syncthreads();
 }
 
+// bit d of a set that lives in shared memory: with several words, one 32-bit load of the half-word that
+// holds it instead of loading the whole set and selecting the word
+template <int W>
+__device__ __forceinline__ int es_smem_bit(const Bits<W>* p, int d) {
+    if (W == 1) return (int)p->test(d);
+    return (int)((((const unsigned int*)p)[d >> 5] >> (d & 31)) & 1u);
+}
+
 // receiver-side availability bits of slot d for an owner: holiday (+ missing skill)
 template <int W, bool MULTI>
 __device__ __forceinline__ int es_avoid_bits(const EsSmemT<W>& s, int slot, int d) {
-    int r = (int)s.shol[slot].test(d);
-    if (MULTI) r += (int)s.sunsk[slot].test(d);
+    int r = es_smem_bit(&s.shol[slot], d);
+    if (MULTI) r += es_smem_bit(&s.sunsk[slot], d);
     return r;
 }
 
@@ -606,6 +617,12 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
             if (MULTI) s.sunsk[slot] = unsk[e];
             s.srk[2 * slot] = (unsigned char)occT.rank_below(t);
             s.srk[2 * slot + 1] = (unsigned char)__popcll(occW & ((1ull << w) - 1ull));
+            if (W > 1) {
+                u64 pk = 0;  // five byte counts in one 64-bit store
+#pragma unroll
+                for (int k = 0; k < 5; ++k) pk |= (u64)(m & K.wd[k]).popc() << (8 * k);
+                *(u64*)(s.swd + 8 * slot) = pk;
+            }
             const EsWin<W> win = es_windows<W, MULTI>(s, K, m);
             const EsEq<W> q = es_eq(s, slot);
             q[0] = win.eq3_14;
@@ -742,7 +759,8 @@ __device__ __forceinline__ unsigned int es_change_present_v(const EsSmemT<W>& s,
              (bits_lo<WD>(q[0]) & bits_lo<WD>(s.cont14[d])).popc();
     if (MULTI) gh += (m & s.partx[d]).popc();
     const int gs = (bits_lo<WD>(q[2]) & bits_lo<WD>(s.cont7[d])).popc();
-    const int cn = (m & s.wdm[d]).popc();
+    // the receiver's slots on d's weekday: a table lookup instead of a W-word popcount
+    const int cn = W > 1 ? (int)s.swd[8 * slot + (int)s.dwd[d]] : (m & s.wdm[d]).popc();
     const int s2 = (int)s.s2t[d * Dm::CBINS + cn];
     ga = (unsigned)gh | ((unsigned)gs << 5) | ((unsigned)(s2 + 32) << 8);
     return s.base[d] + ((unsigned)gh << 16) +
@@ -817,8 +835,13 @@ __device__ __forceinline__ unsigned int es_swap_from_table(const EsSmemT<W>& s, 
     int ds = (int)((g12 >> 5) & 7u) + (int)((g21 >> 5) & 7u) + (int)(b1 & 0xffffu) + (int)(b2 & 0xffffu) - 0x10000;
     const int gap = MULTI ? (int)s.sday[d2] - (int)s.sday[d1] : d2 - d1;
     if (gap < 14) {
-        if (s.part[d1].test(d2)) dh -= 2;
-        if (MULTI && s.partx[d1].test(d2)) dh -= 2;
+        if (W == 1) {
+            if (s.part[d1].test(d2)) dh -= 2;
+            if (MULTI && s.partx[d1].test(d2)) dh -= 2;
+        } else {
+            dh -= 2 * es_smem_bit(&s.part[d1], d2);
+            if (MULTI) dh -= 2 * es_smem_bit(&s.partx[d1], d2);
+        }
         const EsEq<W> q1 = es_eq(s, s1), q2 = es_eq(s, s2);
         const Bits<WD> both14 = bits_lo<WD>(s.cont14[d1]) & bits_lo<WD>(s.cont14[d2]);
         if (both14.any())
