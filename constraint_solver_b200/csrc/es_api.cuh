@@ -12,6 +12,7 @@ struct cs_es_handle {
     int W = 1;                // 64-bit words per slot mask
     bool multi = false;       // slot-generalised extension (S > 1 or a skill table with a gap)
     int wd = 1;               // words that hold the day-indexed sets: ceil(D / 64) <= W
+    bool pk = false;          // <= 38 days: the 14- and 7-day window sets share one word (ES_PK_MAX_DAYS)
     int dp = 0;               // T rounded up to 4 (stride of the per-slot constant tables)
     int stride = 0;           // T + 1 slots (phantom last)
     int threads = 128;
@@ -171,10 +172,15 @@ void es_check_range(cs_es_handle* h, uint32_t first, uint32_t count) {
 // sets cut to ceil(days / 64) words (several shifts per day: fewer days than slots)
 template <int W, bool MULTI>
 void (*es_step_fn(const cs_es_handle* h))(EsParamsT<W>) {
+    const bool pk = h->pk;
     if constexpr (!MULTI) {
         if (h->ref_mode) return es_step_kernel<W, false, true>;
+        if constexpr (W == 1) {
+            if (pk) return es_step_kernel<1, false, false, 1, true>;
+        }
         return es_step_kernel<W, false, false>;
     } else {
+        if (h->wd == 1 && pk) return es_step_kernel<W, true, false, 1, true>;
         if (h->wd == 1) return es_step_kernel<W, true, false, 1>;
         if constexpr (W >= 3) {
             if (h->wd == 2) return es_step_kernel<W, true, false, 2>;
@@ -387,6 +393,7 @@ extern "C" int32_t cs_es_create_ex(const cs_es_config* cfg, const int64_t* emplo
     h->W = (T + 63) / 64;
     h->multi = multi;
     h->wd = (D + 63) / 64;
+    h->pk = D <= ES_PK_MAX_DAYS && !std::getenv("CS_ES_NO_PACKED_DAY_SETS");  // the knob is for A/B timing
     h->dp = (T + 3) & ~3;
     const int32_t rc = guarded(h, [&] {
         const int W = h->W, dp = h->dp;

@@ -265,6 +265,15 @@ struct EsEq {
     int ns;
     __device__ __forceinline__ Bits<W>& operator[](int k) const { return base[k * ns]; }
 };
+// PK ("packed day sets"): a rota of at most 38 days has at most 25 14-day and 32 7-day window starts, so
+// both families share one 64-bit word -- 14-day sets in bits 0..31, 7-day sets in bits 32..63.  The step
+// kernel then keeps CONT[d] = cont14 | cont7 << 32 in cont14[d].w[0] and, per owner, the "one more slot is a
+// violation" planes eq3_14 | eq2_7 << 32 in q[0] and the "one slot fewer ends a violation" planes
+// eq4_14 | eq3_7 << 32 in q[1]: one AND and the two half-word popcounts give the hard and the soft count.
+constexpr int ES_PK_MAX_DAYS = 38;
+__device__ __forceinline__ int es_popc_lo(u64 x) { return __popc((unsigned int)x); }
+__device__ __forceinline__ int es_popc_hi(u64 x) { return __popc((unsigned int)(x >> 32)); }
+
 template <int W>
 __device__ __forceinline__ EsEq<W> es_eq(const EsSmemT<W>& s, int slot) {
     return EsEq<W>{s.eq + slot, s.ns};
@@ -590,7 +599,7 @@ __device__ __forceinline__ int es_avoid_bits(const EsSmemT<W>& s, int slot, int 
 
 // Once per chain-step (masks + tallies must be current).  Everything is per slot or per
 // (slot, value in use): no loop over the employee table.
-template <int W, bool MULTI, int WD = W>
+template <int W, bool MULTI, int WD = W, bool PK = false>
 __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits<W>* __restrict__ hol,
                            const Bits<W>* __restrict__ unsk) {
     typedef EsDim<W> Dm;
@@ -625,10 +634,15 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
             }
             const EsWin<W> win = es_windows<W, MULTI>(s, K, m);
             const EsEq<W> q = es_eq(s, slot);
-            q[0] = win.eq3_14;
-            q[1] = win.eq4_14;
-            q[2] = win.eq2_7;
-            q[3] = win.eq3_7;
+            if (PK) {
+                q[0].w[0] = win.eq3_14.w[0] | (win.eq2_7.w[0] << 32);
+                q[1].w[0] = win.eq4_14.w[0] | (win.eq3_7.w[0] << 32);
+            } else {
+                q[0] = win.eq3_14;
+                q[1] = win.eq4_14;
+                q[2] = win.eq2_7;
+                q[3] = win.eq3_7;
+            }
         }
     }
     // rank -> value lists of the total / weekend counts in use (j-th set bit), and per weekday the
@@ -661,10 +675,17 @@ __device__ void es_prepare(const EsSmemT<W>& s, const EsConstT<W>& K, const Bits
             const int slot = s.dslot[d];
             const Bits<W> m = s.smask[slot];
             const EsEq<W> q = es_eq(s, slot);
-            int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() +
-                        (bits_lo<WD>(q[1]) & bits_lo<WD>(s.cont14[d])).popc();
+            int lossH = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc();
             if (MULTI) lossH += (m & s.partx[d]).popc();
-            const int lossS = (bits_lo<WD>(q[3]) & bits_lo<WD>(s.cont7[d])).popc();
+            int lossS;
+            if (PK) {
+                const u64 x = q[1].w[0] & s.cont14[d].w[0];
+                lossH += es_popc_lo(x);
+                lossS = es_popc_hi(x);
+            } else {
+                lossH += (bits_lo<WD>(q[1]) & bits_lo<WD>(s.cont14[d])).popc();
+                lossS = (bits_lo<WD>(q[3]) & bits_lo<WD>(s.cont7[d])).popc();
+            }
             s.base[d] = ((unsigned)(0x8000 - lossH) << 16) | (unsigned)(0x8000 - lossS);
             // an absent receiver: no pairs, no window counts, zero slots anywhere
             const int to = s.dayb[d], wo = s.dayb[s.dp + d], wd = s.dwd[d];
@@ -750,15 +771,22 @@ __device__ __forceinline__ unsigned int es_w_to_v(unsigned int w) {
 // WD: words that hold the DAY-indexed sets (window starts: cont14 / cont7 / the "count == k" planes).  With
 // several shifts per day a rota of T <= 64 W slots has only T / S days, so those sets are empty above word
 // WD = ceil(D / 64) and their popcounts run on WD words instead of W.
-template <int W, bool MULTI, int WD = W>
+template <int W, bool MULTI, int WD = W, bool PK = false>
 __device__ __forceinline__ unsigned int es_change_present_v(const EsSmemT<W>& s, int d, int slot, unsigned int& ga) {
     typedef EsDim<W> Dm;
     const Bits<W> m = s.smask[slot];
     const EsEq<W> q = es_eq(s, slot);
-    int gh = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc() +
-             (bits_lo<WD>(q[0]) & bits_lo<WD>(s.cont14[d])).popc();
+    int gh = es_avoid_bits<W, MULTI>(s, slot, d) + (m & s.part[d]).popc();
     if (MULTI) gh += (m & s.partx[d]).popc();
-    const int gs = (bits_lo<WD>(q[2]) & bits_lo<WD>(s.cont7[d])).popc();
+    int gs;
+    if (PK) {
+        const u64 x = q[0].w[0] & s.cont14[d].w[0];
+        gh += es_popc_lo(x);
+        gs = es_popc_hi(x);
+    } else {
+        gh += (bits_lo<WD>(q[0]) & bits_lo<WD>(s.cont14[d])).popc();
+        gs = (bits_lo<WD>(q[2]) & bits_lo<WD>(s.cont7[d])).popc();
+    }
     // the receiver's slots on d's weekday: a table lookup instead of a W-word popcount
     const int cn = W > 1 ? (int)s.swd[8 * slot + (int)s.dwd[d]] : (m & s.wdm[d]).popc();
     const int s2 = (int)s.s2t[d * Dm::CBINS + cn];
@@ -825,7 +853,7 @@ __device__ __forceinline__ unsigned int es_swap_v(const EsSmemT<W>& s, const EsC
 // transfers, slot d1 -> e2 and slot d2 -> e1; their tabulated gains/losses are exact except where
 // both slots meet -- the H2/H3 (and same-day) pair (d1, d2) itself and the windows holding BOTH
 // days, whose counts do not change.
-template <int W, bool MULTI, int WD = W>
+template <int W, bool MULTI, int WD = W, bool PK = false>
 __device__ __forceinline__ unsigned int es_swap_from_table(const EsSmemT<W>& s, int d1, int d2) {
     typedef EsDim<W> Dm;
     const int s1 = s.dslot[d1], s2 = s.dslot[d2];
@@ -843,14 +871,23 @@ __device__ __forceinline__ unsigned int es_swap_from_table(const EsSmemT<W>& s, 
             if (MULTI) dh -= 2 * es_smem_bit(&s.partx[d1], d2);
         }
         const EsEq<W> q1 = es_eq(s, s1), q2 = es_eq(s, s2);
-        const Bits<WD> both14 = bits_lo<WD>(s.cont14[d1]) & bits_lo<WD>(s.cont14[d2]);
-        if (both14.any())
-            dh += (bits_lo<WD>(q1[1]) & both14).popc() - (bits_lo<WD>(q1[0]) & both14).popc() +
-                  (bits_lo<WD>(q2[1]) & both14).popc() - (bits_lo<WD>(q2[0]) & both14).popc();
-        const Bits<WD> both7 = bits_lo<WD>(s.cont7[d1]) & bits_lo<WD>(s.cont7[d2]);
-        if (both7.any())
-            ds += (bits_lo<WD>(q1[3]) & both7).popc() - (bits_lo<WD>(q1[2]) & both7).popc() +
-                  (bits_lo<WD>(q2[3]) & both7).popc() - (bits_lo<WD>(q2[2]) & both7).popc();
+        if (PK) {
+            const u64 both = s.cont14[d1].w[0] & s.cont14[d2].w[0];  // the windows (both lengths) holding both days
+            if (both) {
+                const u64 l1 = q1[1].w[0] & both, g1 = q1[0].w[0] & both, l2 = q2[1].w[0] & both, g2 = q2[0].w[0] & both;
+                dh += es_popc_lo(l1) - es_popc_lo(g1) + es_popc_lo(l2) - es_popc_lo(g2);
+                ds += es_popc_hi(l1) - es_popc_hi(g1) + es_popc_hi(l2) - es_popc_hi(g2);
+            }
+        } else {
+            const Bits<WD> both14 = bits_lo<WD>(s.cont14[d1]) & bits_lo<WD>(s.cont14[d2]);
+            if (both14.any())
+                dh += (bits_lo<WD>(q1[1]) & both14).popc() - (bits_lo<WD>(q1[0]) & both14).popc() +
+                      (bits_lo<WD>(q2[1]) & both14).popc() - (bits_lo<WD>(q2[0]) & both14).popc();
+            const Bits<WD> both7 = bits_lo<WD>(s.cont7[d1]) & bits_lo<WD>(s.cont7[d2]);
+            if (both7.any())
+                ds += (bits_lo<WD>(q1[3]) & both7).popc() - (bits_lo<WD>(q1[2]) & both7).popc() +
+                      (bits_lo<WD>(q2[3]) & both7).popc() - (bits_lo<WD>(q2[2]) & both7).popc();
+        }
     }
     const int wd1 = s.dwd[d1], wd2 = s.dwd[d2];
     if (wd1 != wd2) {
@@ -897,7 +934,7 @@ __device__ __forceinline__ long long es_block_min(long long key, u64* red) {
 //   B  change moves to ABSENT employees   (thread per employee, loop over slots; the value is the
 //      per-slot table entry plus the employee's holiday / skill bits, tracked with one min per candidate)
 //   C  swaps
-template <int W, bool MULTI, bool DUMP, int WD = W>
+template <int W, bool MULTI, bool DUMP, int WD = W, bool PK = false>
 __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT<W>& K,
                                              const Bits<W>* __restrict__ hol, const Bits<W>* __restrict__ unsk,
                                              const u64* __restrict__ cnt2,
@@ -915,7 +952,7 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
             const int id = d * E + (int)s.semp[slot];
             if ((int)s.dslot[d] != slot) {
                 unsigned int ga;
-                const unsigned int v = es_change_present_v<W, MULTI, WD>(s, d, slot, ga);
+                const unsigned int v = es_change_present_v<W, MULTI, WD, PK>(s, d, slot, ga);
                 s.ga[d * s.ns + slot] = (uint16_t)ga;
                 const long long k2 = es_key(v, id);
                 key = k2 < key ? k2 : key;
@@ -1024,7 +1061,7 @@ __device__ __forceinline__ long long es_scan(const EsSmemT<W>& s, const EsConstT
             const int dd = scan[r], d1 = dd >> 8, d2 = dd & 0xff;
             const int id = n_change + es_tri_index(T, d1, d2);
             if (s.dslot[d1] != s.dslot[d2]) {
-                const unsigned int v = es_swap_from_table<W, MULTI, WD>(s, d1, d2);
+                const unsigned int v = es_swap_from_table<W, MULTI, WD, PK>(s, d1, d2);
                 const long long k2 = es_key(v, id);
                 key = k2 < key ? k2 : key;
                 if (DUMP) {
@@ -1167,7 +1204,7 @@ __device__ long long es_scan_ref(const EsSmemT<W>& s, const EsConstT<W>& K, cons
 }
 
 // per-slot constants of the handle: part | cont14 | cont7 | partx from the host table, weekday masks
-template <int W, bool MULTI>
+template <int W, bool MULTI, bool PK = false>
 __device__ __forceinline__ void es_load_consts(const EsSmemT<W>& s, const EsConstT<W>& K,
                                                const Bits<W>* __restrict__ slotc) {
     for (int d = threadIdx.x; d < s.dp; d += blockDim.x) {
@@ -1176,6 +1213,7 @@ __device__ __forceinline__ void es_load_consts(const EsSmemT<W>& s, const EsCons
         s.part[d] = slotc[d];
         s.cont14[d] = slotc[s.dp + d];
         s.cont7[d] = slotc[2 * s.dp + d];
+        if (PK) s.cont14[d].w[0] |= slotc[2 * s.dp + d].w[0] << 32;
         if (MULTI) s.partx[d] = slotc[3 * s.dp + d];
         s.wdm[d] = (d < K.T && wd < 5) ? K.wd[wd] : Bits<W>::zero();
         s.dwd[d] = (unsigned char)wd;
@@ -1187,15 +1225,16 @@ __device__ __forceinline__ void es_load_consts(const EsSmemT<W>& s, const EsCons
 #define ES_LB_THREADS(W, MULTI) (((W) == 1 && !(MULTI)) ? 256 : 512)
 #define ES_LB_BLOCKS(W, MULTI) (((W) == 1 && !(MULTI)) ? 4 : 1)
 
-template <int W, bool MULTI, bool REF, int WD = W>
+template <int W, bool MULTI, bool REF, int WD = W, bool PK = false>
 __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI)) es_step_kernel(EsParamsT<W> p) {
+    static_assert(!(PK && (REF || WD != 1)), "packed day sets: one day word, full-neighbourhood scan only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EsConstT<W>& K = p.K;
     const EsSmemT<W> s = es_carve<W, MULTI>(smem_raw, K.T, K.E);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int T = K.T, E = K.E;
     const int n_change = T * E, n_swap = T * (T - 1) / 2;
-    es_load_consts<W, MULTI>(s, K, p.slotc);
+    es_load_consts<W, MULTI, PK>(s, K, p.slotc);
     es_zero_masks(s, E);
 
     for (;;) {
@@ -1228,7 +1267,7 @@ __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI
                 best_s = 0;
                 break;
             }
-            es_prepare<W, MULTI, WD>(s, K, p.hol, p.unsk);
+            es_prepare<W, MULTI, WD, PK>(s, K, p.hol, p.unsk);
             // non-identity candidates: every (slot, employee != current) + every slot pair held by
             // two different employees -- each of them is evaluated by es_scan
             long long key;
@@ -1238,8 +1277,8 @@ __global__ void __launch_bounds__(ES_LB_THREADS(W, MULTI), ES_LB_BLOCKS(W, MULTI
                 scored += nsc;
             } else {
                 scored += (unsigned long long)(n_change - T) + (unsigned long long)(n_swap - s.misc[ES_SAME]);
-                key = p.dump_h ? es_scan<W, MULTI, true, WD>(s, K, p.hol, p.unsk, p.cnt2, p.tri_scan, p.dump_h, p.dump_s)
-                               : es_scan<W, MULTI, false, WD>(s, K, p.hol, p.unsk, p.cnt2, p.tri_scan, nullptr, nullptr);
+                key = p.dump_h ? es_scan<W, MULTI, true, WD, PK>(s, K, p.hol, p.unsk, p.cnt2, p.tri_scan, p.dump_h, p.dump_s)
+                               : es_scan<W, MULTI, false, WD, PK>(s, K, p.hol, p.unsk, p.cnt2, p.tri_scan, nullptr, nullptr);
                 key = es_block_min(key, s.red);
             }
             if (p.dump_h) break;
