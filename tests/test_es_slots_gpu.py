@@ -262,3 +262,40 @@ def test_random_slot_instances_every_delta_and_trajectory():
             assert np.array_equal(mv["kind"], ref["trace_kind"]) and np.array_equal(mv["a"], ref["trace_x"])
             assert np.array_equal(mv["b"], ref["trace_y"])
             assert np.array_equal(th, ref["trace_hard"]) and np.array_equal(ts, ref["trace_soft"])
+
+
+def test_packed_day_sets_equal_plain_sets_up_to_the_38_day_limit(monkeypatch):
+    """Rotas of <= 38 days keep the 14- and 7-day window sets in one word (step kernel, PK).  Every
+    candidate's delta and a 25-step trajectory must equal the plain-set kernel's (the knob) and the
+    oracle's, at the limit itself (38 days: 7-day window start 31 = bit 63), one past it (39: not
+    packed) and with several shifts per day."""
+    rng = np.random.default_rng(38)
+    for D, S, E in [(38, 1, 6), (38, 3, 9), (37, 2, 5), (39, 1, 6), (31, 1, 7), (14, 3, 4), (13, 1, 3), (7, 2, 3)]:
+        ids = np.arange(E, dtype=np.int64) * 3 + 1
+        hol = sorted({(int(ids[rng.integers(0, E)]), int(rng.integers(0, D))) for _ in range(E)})
+        kw = dict(holidays=hol, n_chains=6, seed=D * 10 + S, trace_capacity=32, start_weekday=int(rng.integers(0, 7)))
+        if S > 1:
+            kw.update(shifts_per_day=S, skills=[int(rng.integers(1, 1 << S)) for _ in range(E)])
+        out = []
+        for knob in (None, "1"):
+            if knob is None:
+                monkeypatch.delenv("CS_ES_NO_PACKED_DAY_SETS", raising=False)
+            else:
+                monkeypatch.setenv("CS_ES_NO_PACKED_DAY_SETS", knob)
+            with cs.ScheduleChains(D, ids, **kw) as e:
+                e.init_random()
+                start = e.get_chains()
+                dh, ds = e.neighbourhood_deltas(0)
+                e.step(25)
+                out.append((start, dh, ds, e.get_chains(), e.scores(), [e.trace(k) for k in range(6)]))
+        a, b = out
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), (D, S)
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4][0], b[4][0]) and np.array_equal(a[4][1], b[4][1])
+        for ta, tb in zip(a[5], b[5]):
+            assert all(np.array_equal(x, y) for x, y in zip(ta[:3], tb[:3])), (D, S)
+        T = D * S
+        if S == 1:
+            rh, rs = orc.es_neighbourhood_deltas(a[0][0][:T], ids, kw["start_weekday"], hol)
+        else:
+            rh, rs = orc.esx_neighbourhood_deltas(a[0][0][:T], ids, D, S, kw["start_weekday"], hol, kw["skills"])
+        assert np.array_equal(a[1], rh) and np.array_equal(a[2], rs), (D, S)
