@@ -138,3 +138,21 @@ def test_rust_shim_implements_the_reference_trait_surface():
     used = set(re.findall(r"ffi::(cs_[a-z0-9_]+)\(", tr))
     assert used and used <= declared, used - declared
     assert "pub mod traits;" in open(os.path.join(root, "lib.rs")).read()
+
+
+def test_bench_helpers_are_deterministic_and_median_is_honest():
+    """bench.py host logic that needs no GPU: the synthetic scheduling instances are a pure function
+    of (name, seed), and the time-to-best median refuses to summarise runs that mostly failed."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    w1, ids1, hol1, sk1 = bench.es_instance("es2000x3", 42)
+    w2, ids2, hol2, sk2 = bench.es_instance("es2000x3", 42)
+    assert (w1, hol1) == (w2, hol2) and list(ids1) == list(ids2) and list(sk1) == list(sk2)
+    assert w1["D"] * w1["S"] == 168 and len(hol1) == w1["E"] * w1["nhol"]
+    assert all(0 < int(s) < (1 << w1["S"]) for s in sk1)          # everybody qualified for something
+    assert bench.es_instance("es50", 42)[3] is None                # reference rotas carry no skill table
+    assert bench._median([3.0, 1.0, 2.0]) == 2.0 and bench._median([1.0, None, 3.0, 2.0, 5.0]) == 2.5
+    assert bench._median([None, None, 1.0]) is None and bench._median([]) is None
